@@ -1,0 +1,170 @@
+/*
+ * nfb200.h -- C ABI of libnfb200.so: B200 (sm_100a) kernels for the normalizing-flow hot path
+ * of tatsy/normalizing-flows-pytorch (flow-layer forward / inverse + per-sample log|det J|).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer to contiguous fp32 data unless stated otherwise; the caller
+ *     owns all memory.  No allocation, no host synchronisation, no stdout: every entry point only
+ *     enqueues kernels on `stream` (a cudaStream_t passed as void*), so a whole stack is capturable
+ *     in a CUDA graph.
+ *   - Return value: 0 = success; > 0 = the cudaError_t of the launch; < 0 = argument error
+ *     (NFB_ERR_*).  nfb_error_string() maps any of them to text.  Nothing throws across the ABI.
+ *   - "z" tensors are (B, C, H, W) contiguous (NCHW) or (B, C) with H = W = 1.  D = C*H*W.
+ *   - Log-det: `ldj_out[b] = ldj_in[b] + delta_b`.  Pass the same pointer twice for the reference's
+ *     in-place `log_df_dz += ...` (coupling.py:110, modules.py:249,480); pass a different buffer for
+ *     the layers that return a new tensor (Logit, modules.py:150).
+ *   - z_out may alias z_in (in-place update of the transformed half; the pass-through half is then
+ *     not touched at all).
+ *   - Split modes (AbstractCoupling.__init__, coupling.py:16-30; index formulas in DESIGN.md):
+ *       NFB_SPLIT_1D       squeeze1d / unsqueeze1d      (squeeze.py:64-83)   z0 = even entries
+ *       NFB_SPLIT_CHECKER  checker_split / checker_merge (squeeze.py:32-61)  space-to-depth, blocks (a,d)|(b,c)
+ *       NFB_SPLIT_CHANNEL  channel_split / channel_merge (squeeze.py:5-17)   first half | second half
+ *     `odd` != 0 swaps the roles of the two halves.
+ *   - The conditioner output `params` is the (B, P*c0, h, w) tensor the reference's `self.net(z1)`
+ *     returns (coupling.py:105,176), consumed in place -- no slicing copies.
+ */
+#ifndef NFB200_H_
+#define NFB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nfb_stream_t; /* cudaStream_t */
+
+#define NFB_SPLIT_1D 0
+#define NFB_SPLIT_CHECKER 1
+#define NFB_SPLIT_CHANNEL 2
+
+#define NFB_OK 0
+#define NFB_ERR_NULL (-1)        /* required pointer is NULL */
+#define NFB_ERR_SHAPE (-2)       /* non-positive or inconsistent dimension */
+#define NFB_ERR_SPLIT (-3)       /* shape not splittable in this mode (odd H/W or odd C): squeeze.py view/split would fail */
+#define NFB_ERR_UNSUPPORTED (-4) /* valid request outside what the kernels implement (e.g. K > NFB_MAX_MIXTURES) */
+
+#define NFB_MAX_MIXTURES 32
+#define NFB_MAX_BINS 32
+
+int nfb_version(void);
+const char* nfb_error_string(int code);
+/* number of kernel launches enqueued by this library since load (all entry points); for bench accounting */
+unsigned long long nfb_launch_count(void);
+
+/* ---------------- coupling bijections (coupling.py) ---------------- */
+
+/* AffineCoupling._transform (coupling.py:104-112): s = tanh(s_raw)*a + b; z0' = z0*exp(s) + t; ldj += sum(s).
+ * params = (B, 2*c0, h, w): channels [0,c0) = t, [c0,2c0) = s_raw.  s_log_scale / s_bias: device scalars. */
+int nfb_affine_coupling_fwd(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                            float* ldj_out, const float* s_log_scale, const float* s_bias, int B, int C, int H,
+                            int W, int mode, int odd, nfb_stream_t stream);
+/* AffineCoupling._inverse_transform (coupling.py:114-122): y0' = exp(-s)*(y0 - t); ldj -= sum(s). */
+int nfb_affine_coupling_inv(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                            float* ldj_out, const float* s_log_scale, const float* s_bias, int B, int C, int H,
+                            int W, int mode, int odd, nfb_stream_t stream);
+
+/* AdditiveCoupling (coupling.py:69-79): z0' = z0 + sign*t; params = (B, c0, h, w) = t.  No log-det. */
+int nfb_additive_coupling(const float* z_in, float* z_out, const float* params, float sign, int B, int C, int H,
+                          int W, int mode, int odd, nfb_stream_t stream);
+
+/* MixLogAttnCoupling._transform (coupling.py:172-190) incl. MixLogCDF.forward (modules.py:190-194) and
+ * Logit(1e-5).forward: params = (B, (2+3K)*c0, h, w), sections [a | b | logpi(K) | mu(K) | s(K)],
+ * mixture channel = k*c0 + m (coupling.py:180-182). */
+int nfb_mixlog_coupling_fwd(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                            float* ldj_out, const float* a_log_scale, const float* a_bias, int B, int C, int H,
+                            int W, int mode, int odd, int K, nfb_stream_t stream);
+/* MixLogAttnCoupling._inverse_transform (coupling.py:192-210) incl. the bisection of MixLogCDF.backward
+ * (modules.py:196-212).  The reference stops after 25 iterations when every element has converged and runs
+ * all 100 when any element stalls (val == x); `stall_flag` (device int, zeroed by the call) reproduces that
+ * global rule without a host sync: phase 1 runs 25 iterations and raises the flag on a stall, phase 2 (same
+ * call) continues to 100 iterations only if the flag is set.  scratch: 2*B*n0 floats (lo/hi). */
+int nfb_mixlog_coupling_inv(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                            float* ldj_out, const float* a_log_scale, const float* a_bias, float* scratch,
+                            int* stall_flag, int B, int C, int H, int W, int mode, int odd, int K,
+                            nfb_stream_t stream);
+
+/* Rational-quadratic spline coupling (Durkan et al. 2019; no counterpart in the reference -- parity unpinned):
+ * params = (B, (3K-1)*c0, h, w), sections [widths(K) | heights(K) | derivatives(K-1)], bin channel = k*c0 + m;
+ * identity outside [-bound, bound], boundary derivatives 1. */
+int nfb_rqs_coupling_fwd(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                         float* ldj_out, int B, int C, int H, int W, int mode, int odd, int K, float bound,
+                         nfb_stream_t stream);
+int nfb_rqs_coupling_inv(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                         float* ldj_out, int B, int C, int H, int W, int mode, int odd, int K, float bound,
+                         nfb_stream_t stream);
+
+/* squeeze (split) / unsqueeze (merge) of AbstractCoupling (coupling.py:33,35): bit-exact permutations.
+ * z0_out / z1_out are (B, c0, h, w) contiguous; either may be NULL to skip it. */
+int nfb_coupling_split(const float* z, float* z0_out, float* z1_out, int B, int C, int H, int W, int mode,
+                       int odd, nfb_stream_t stream);
+int nfb_coupling_merge(const float* z0, const float* z1, float* z_out, int B, int C, int H, int W, int mode,
+                       int odd, nfb_stream_t stream);
+
+/* ---------------- per-channel affine layers (modules.py) ---------------- */
+
+/* ActNorm.forward (modules.py:246-250): z = (z - bias)/exp(log_scale); ldj -= sum(log_scale)*HW. */
+int nfb_actnorm_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* log_scale,
+                    const float* bias, int B, int C, int HW, nfb_stream_t stream);
+/* ActNorm.backward (modules.py:252-256): y = y*exp(log_scale) + bias; ldj += sum(log_scale)*HW. */
+int nfb_actnorm_inv(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* log_scale,
+                    const float* bias, int B, int C, int HW, nfb_stream_t stream);
+/* ActNorm data-dependent init (modules.py:238-244): log_scale = log(std_unbiased + eps), bias = mean. */
+int nfb_actnorm_init(const float* z, float* log_scale_out, float* bias_out, int B, int C, int HW, float eps,
+                     nfb_stream_t stream);
+/* flow BatchNorm.forward (modules.py:300-305): x = (x-mean)/sqrt(var)*exp(log_gamma)+beta;
+ * ldj += sum(log_gamma - 0.5 log var)*HW. */
+int nfb_bnflow_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* mean,
+                   const float* var, const float* log_gamma, const float* beta, int B, int C, int HW,
+                   nfb_stream_t stream);
+/* flow BatchNorm.backward (modules.py:315-320). */
+int nfb_bnflow_inv(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* mean,
+                   const float* var, const float* log_gamma, const float* beta, int B, int C, int HW,
+                   nfb_stream_t stream);
+/* flow BatchNorm train-mode statistics (modules.py:285-287): mean, biased variance + eps. */
+int nfb_bnflow_batch_stats(const float* z, float* mean_out, float* var_out, int B, int C, int HW, float eps,
+                           nfb_stream_t stream);
+
+/* Logit.forward (modules.py:146-150): x = clamp(x, lo, hi); y = logit(x); ldj += sum(-(y - 2 softplus(y))). */
+int nfb_logit_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, float lo, float hi, int B,
+                  int D, nfb_stream_t stream);
+/* Logit.backward (modules.py:152-155): sigmoid; ldj += sum(x - 2 softplus(x)). */
+int nfb_logit_inv(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, int B, int D,
+                  nfb_stream_t stream);
+
+/* ---------------- invertible 1x1 convolution (modules.py:441-497) ---------------- */
+
+/* W = P (L o tril + I)(U o triu + diag(sign_s exp(log_s)))  (modules.py:471-473) -> W_out (C*C, row-major);
+ * if Winv_out != NULL also W^-1 = U'^-1 L'^-1 P^T (fp64 substitution on the device, rounded once) which
+ * replaces the per-call lu_solve of modules.py:490. */
+int nfb_invconv1x1_weight(const float* P, const float* L, const float* U, const float* log_s,
+                          const float* sign_s, float* W_out, float* Winv_out, int C, nfb_stream_t stream);
+/* out[b,:,p] = M @ z[b,:,p]; ldj += sign * sum(log_s) * HW.  forward: M = W, sign = +1 (modules.py:477-480);
+ * inverse: M = W^-1, sign = -1 (modules.py:490-495).  z_out must NOT alias z_in. */
+int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
+                         const float* log_s, float sign, int B, int C, int HW, nfb_stream_t stream);
+
+/* ---------------- Squeeze2d / Unsqueeze2d (squeeze.py:153-189) ---------------- */
+
+/* (B,C,H,W) -> (B,4C,H/2,W/2): out[b,4c+2dy+dx,i,j] = in[b,c,2i+dy,2j+dx]; odd swaps the two channel halves. */
+int nfb_squeeze2d(const float* z_in, float* z_out, int B, int C, int H, int W, int odd, nfb_stream_t stream);
+/* exact inverse; C, H, W are those of the UNSQUEEZED (output) tensor. */
+int nfb_unsqueeze2d(const float* z_in, float* z_out, int B, int C, int H, int W, int odd, nfb_stream_t stream);
+
+/* ---------------- likelihood (main.py:83-85) ---------------- */
+
+/* nll_rows[b] = 0.5*||z_b||^2 + 0.5*D*log(2 pi) - ldj[b]  (= -(log N(z_b;0,I) + ldj_b)), ||z||^2 accumulated in
+ * fp64 and rounded once.  nll_rows (device float[B]) is required.  sum_out (device double[2], may be NULL) =
+ * { sum_b nll_rows[b] in fp64 (fixed order: deterministic), B } -- the 2-element payload that is all-reduced
+ * across GPUs. */
+int nfb_gauss_nll(const float* z, const float* ldj, float* nll_rows, double* sum_out, int B, int D,
+                  nfb_stream_t stream);
+
+/* ---------------- conditioner networks (modules.py:342-438, weight_norm.py) ---------------- */
+
+/* Fold WeightNorm (weight_norm.py:40: w = v*g/(||v||_dim0 + eps)) of one conv/linear weight:
+ * v (O, I*kk), g (I*kk) -> w_out (O, I*kk). */
+int nfb_weight_norm(const float* v, const float* g, float* w_out, int O, int Ikk, float eps, nfb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFB200_H_ */

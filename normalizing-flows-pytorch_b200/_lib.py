@@ -1,0 +1,101 @@
+"""ctypes binding of libnfb200.so (the C ABI declared in include/nfb200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a tensor is not a CUDA fp32
+tensor the call raises.  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnfb200.so')
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'nfb200.h')
+
+SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
+
+_P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes (all return int unless listed in _RESTYPES)
+_SIGNATURES = {
+    'nfb_version': [],
+    'nfb_error_string': [_I],
+    'nfb_launch_count': [],
+    'nfb_affine_coupling_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_affine_coupling_inv': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_additive_coupling': [_P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_mixlog_coupling_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_mixlog_coupling_inv': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_rqs_coupling_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'nfb_rqs_coupling_inv': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'nfb_coupling_split': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_coupling_merge': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_actnorm_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_actnorm_inv': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_actnorm_init': [_P, _P, _P, _I, _I, _I, _F, _P],
+    'nfb_bnflow_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_bnflow_inv': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_bnflow_batch_stats': [_P, _P, _P, _I, _I, _I, _F, _P],
+    'nfb_logit_fwd': [_P, _P, _P, _P, _F, _F, _I, _I, _P],
+    'nfb_logit_inv': [_P, _P, _P, _P, _I, _I, _P],
+    'nfb_invconv1x1_weight': [_P, _P, _P, _P, _P, _P, _P, _I, _P],
+    'nfb_invconv1x1_apply': [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
+    'nfb_squeeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'nfb_unsqueeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'nfb_gauss_nll': [_P, _P, _P, _P, _I, _I, _P],
+    'nfb_weight_norm': [_P, _P, _P, _I, _I, _F, _P],
+}
+_RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name the public header declares (used by the CPU test-suite)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r'\b(nfb_[a-z0-9_]+)\s*\(', text)))
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('libnfb200.so not found at %s -- build it with '
+                               '`python -c "import __graft_entry__ as g; g.build()"` '
+                               '(nfb200 has no CPU / PyTorch fallback path)' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing: loud on purpose
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libnfb200 call failed (%d): %s' % (rc, lib().nfb_error_string(rc).decode()))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dev(t, name='tensor'):
+    """Validate a tensor for the CUDA path and return it contiguous."""
+    if not t.is_cuda:
+        raise RuntimeError('nfb200: %s must live on a CUDA device (no CPU fallback); got %s' % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError('nfb200: %s must be float32; got %s' % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr(t):
+    return t.data_ptr()
+
+
+def launch_count():
+    return int(lib().nfb_launch_count())

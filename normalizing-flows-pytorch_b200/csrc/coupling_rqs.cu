@@ -1,0 +1,150 @@
+// coupling_rqs.cu -- monotonic rational-quadratic spline coupling with identity tails (Durkan et al. 2019,
+// "Neural Spline Flows").  The reference has NO spline coupling: this bijection's parity is
+// unpinned; its specification is oracle/flow_oracle.py:rqs_transform, which this kernel follows op by op.
+//
+// Per transformed element: K unnormalised widths, K heights, K-1 interior derivatives (bin-major channels
+// k*c0 + m, like the reference's mixture layout, coupling.py:180-182).  thread = one element; parameter loads of
+// a warp are contiguous 128-byte lines; the softmaxes, the knot cumsum, the bin search and the rational map all
+// stay in registers; log|dy/dx| is reduced per sample in the same pass.
+#include "common.cuh"
+
+namespace nfb {
+
+constexpr float kMinW = 1.0e-3f, kMinH = 1.0e-3f, kMinD = 1.0e-3f;
+
+// knots[0..K] from K unnormalised logits: min + (1 - min*K) softmax -> cumsum -> scale to [-bound, bound]
+template <int KT>
+__device__ __forceinline__ void rqs_knots(float* knots, const float* __restrict__ base, size_t stride, int K,
+                                          float mn, float bound) {
+    const int kk = KT ? KT : K;
+    float u[KT ? KT : NFB_MAX_BINS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kk; ++k) { u[k] = __ldg(base + k * stride); mx = fmaxf(mx, u[k]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kk; ++k) { u[k] = expf(u[k] - mx); sum += u[k]; }
+    const float scale = 1.f - mn * static_cast<float>(kk);
+    float c = 0.f;
+    knots[0] = -bound;
+#pragma unroll
+    for (int k = 0; k < kk; ++k) {
+        c = __fadd_rn(c, __fadd_rn(mn, __fmul_rn(scale, __fdiv_rn(u[k], sum))));
+        knots[k + 1] = __fsub_rn(__fmul_rn(2.f * bound, c), bound);
+    }
+    knots[kk] = bound;
+}
+
+template <int MODE, int KT, bool INV>
+struct RqsRow {
+    const float* zin;
+    float* zout;
+    const float* __restrict__ params;
+    SplitGeom g;
+    int items;
+    int K;
+    float bound;
+    bool inplace;
+
+    __device__ __forceinline__ float finish(float acc) const { return acc; }
+
+    __device__ __forceinline__ float operator()(int row, int j) const {
+        const int kk = KT ? KT : K;
+        const size_t zbase = static_cast<size_t>(row) * g.D;
+        const size_t n0 = g.n0;
+        const float* prow = params + static_cast<size_t>(row) * (3 * kk - 1) * n0 + j;
+        const int e = half_offset<MODE>(g, j, 0);
+        const float x = zin[zbase + e];
+        if (!inplace) {
+            const int e1 = half_offset<MODE>(g, j, 1);
+            zout[zbase + e1] = zin[zbase + e1];
+        }
+        if (!(x >= -bound && x <= bound)) {  // linear tails: identity, log-det 0
+            zout[zbase + e] = x;
+            return 0.f;
+        }
+        float xk[(KT ? KT : NFB_MAX_BINS) + 1], yk[(KT ? KT : NFB_MAX_BINS) + 1];
+        rqs_knots<KT>(xk, prow, n0, K, kMinW, bound);
+        rqs_knots<KT>(yk, prow + static_cast<size_t>(kk) * n0, n0, K, kMinH, bound);
+        const float* edges = INV ? yk : xk;
+        int bin = 0;
+#pragma unroll
+        for (int k = 1; k < kk; ++k) bin += (x >= edges[k]) ? 1 : 0;
+        float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kk; ++k)  // register select instead of dynamic indexing
+            if (k == bin) { x0 = xk[k]; x1 = xk[k + 1]; y0 = yk[k]; y1 = yk[k + 1]; }
+        const float* dbase = prow + static_cast<size_t>(2 * kk) * n0;
+        const float d0 = bin == 0 ? 1.f : kMinD + softplus_f(__ldg(dbase + static_cast<size_t>(bin - 1) * n0));
+        const float d1 = bin == kk - 1 ? 1.f : kMinD + softplus_f(__ldg(dbase + static_cast<size_t>(bin) * n0));
+        const float w = x1 - x0, h = y1 - y0;
+        const float sk = h / w;
+        float out, ld;
+        if (!INV) {
+            const float xi = (x - x0) / w;
+            const float om = xi * (1.f - xi);
+            const float den = sk + (d1 + d0 - 2.f * sk) * om;
+            out = y0 + h * (sk * xi * xi + d0 * om) / den;
+            ld = 2.f * logf(sk) + logf(d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)) - 2.f * logf(den);
+        } else {
+            const float dy = x - y0;
+            const float t = d0 + d1 - 2.f * sk;
+            const float a = dy * t + h * (sk - d0);
+            const float b = h * d0 - dy * t;
+            const float c = -sk * dy;
+            const float disc = b * b - 4.f * a * c;
+            const float xi = 2.f * c / (-b - sqrtf(disc));
+            out = xi * w + x0;
+            const float om = xi * (1.f - xi);
+            const float den = sk + t * om;
+            ld = -(2.f * logf(sk) + logf(d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)) - 2.f * logf(den));
+        }
+        zout[zbase + e] = out;
+        return ld;
+    }
+};
+
+template <int MODE, int KT, bool INV>
+static int rqs_launch(const float* zi, float* zo, const float* pr, const float* li, float* lo, const SplitGeom& g, int K,
+                      float bound, cudaStream_t st) {
+    RqsRow<MODE, KT, INV> f{zi, zo, pr, g, g.n0, K, bound, zi == zo};
+    return launch_rows(f, li, lo, g.B, st);
+}
+
+template <bool INV>
+static int rqs_entry(const float* z_in, float* z_out, const float* params, const float* ldj_in, float* ldj_out, int B,
+                     int C, int H, int W, int mode, int odd, int K, float bound, nfb_stream_t stream) {
+    if (!z_in || !z_out || !params || !ldj_in || !ldj_out) return NFB_ERR_NULL;
+    if (K < 2 || !(bound > 0.f)) return NFB_ERR_SHAPE;
+    if (K > NFB_MAX_BINS) return NFB_ERR_UNSUPPORTED;
+    SplitGeom g;
+    const int rc = make_geom(g, B, C, H, W, mode, odd);
+    if (rc != NFB_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    switch (mode) {
+        case NFB_SPLIT_1D:
+            return K == 8 ? rqs_launch<NFB_SPLIT_1D, 8, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st)
+                          : rqs_launch<NFB_SPLIT_1D, 0, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st);
+        case NFB_SPLIT_CHECKER:
+            return K == 8 ? rqs_launch<NFB_SPLIT_CHECKER, 8, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st)
+                          : rqs_launch<NFB_SPLIT_CHECKER, 0, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st);
+        default:
+            return K == 8 ? rqs_launch<NFB_SPLIT_CHANNEL, 8, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st)
+                          : rqs_launch<NFB_SPLIT_CHANNEL, 0, INV>(z_in, z_out, params, ldj_in, ldj_out, g, K, bound, st);
+    }
+}
+
+}  // namespace nfb
+
+using namespace nfb;
+
+extern "C" int nfb_rqs_coupling_fwd(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                                    float* ldj_out, int B, int C, int H, int W, int mode, int odd, int K, float bound,
+                                    nfb_stream_t stream) {
+    return rqs_entry<false>(z_in, z_out, params, ldj_in, ldj_out, B, C, H, W, mode, odd, K, bound, stream);
+}
+extern "C" int nfb_rqs_coupling_inv(const float* z_in, float* z_out, const float* params, const float* ldj_in,
+                                    float* ldj_out, int B, int C, int H, int W, int mode, int odd, int K, float bound,
+                                    nfb_stream_t stream) {
+    return rqs_entry<true>(z_in, z_out, params, ldj_in, ldj_out, B, C, H, W, mode, odd, K, bound, stream);
+}

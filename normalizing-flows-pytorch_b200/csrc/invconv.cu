@@ -1,0 +1,202 @@
+// invconv.cu -- InvertibleConv1x1 (modules.py:441-497).
+//   nfb_invconv1x1_weight : W = P (L o tril + I)(U o triu + diag(sign_s exp(log_s)))  and (optionally) W^-1
+//   nfb_invconv1x1_apply  : out[b,:,p] = M z[b,:,p]  (+ the sample-independent log-det sum(log_s) * HW)
+// The contraction is tiny (C in {2,3,12,48,192}) and needs fp32-exact products (bits/dim parity 1e-5 rules out
+// single-pass TF32/BF16 tensor-core math), so it is register-tiled FP32 FFMA with the C x C matrix in shared memory.
+#include "common.cuh"
+
+namespace nfb {
+
+// ---- weight assembly: one CTA; masks and the diagonal are applied on the fly (no staging) ----------------
+constexpr int kMaxInvconvC = 256;
+
+__device__ __forceinline__ float lower_at(const float* __restrict__ L, int C, int r, int c) {  // L o tril(-1) + I
+    return c < r ? __ldg(L + r * C + c) : (c == r ? 1.f : 0.f);
+}
+__device__ __forceinline__ float upper_at(const float* __restrict__ U, const float* diag, int C, int r, int c) {
+    return c > r ? __ldg(U + r * C + c) : (c == r ? diag[r] : 0.f);  // U o triu(1) + diag(sign_s exp(log_s))
+}
+
+__global__ void __launch_bounds__(256) invconv_weight_kernel(const float* __restrict__ P, const float* __restrict__ L,
+                                                            const float* __restrict__ U, const float* __restrict__ log_s,
+                                                            const float* __restrict__ sign_s, float* __restrict__ W,
+                                                            float* __restrict__ Winv, int C) {
+    __shared__ float diag[kMaxInvconvC];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) diag[i] = __fmul_rn(__ldg(sign_s + i), expf(__ldg(log_s + i)));
+    __syncthreads();
+    // W[r,c] = sum_k P[r,k] (L' U')[k,c]   (modules.py:473).  P is a permutation, so only one k contributes.
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int r = i / C, c = i - r * C;
+        float acc = 0.f;
+        for (int k = 0; k < C; ++k) {
+            const float p = __ldg(P + r * C + k);
+            if (p != 0.f) {
+                float t = 0.f;
+                const int jmax = k < c ? k : c;
+                for (int j = 0; j <= jmax; ++j) t = fmaf(lower_at(L, C, k, j), upper_at(U, diag, C, j, c), t);
+                acc = fmaf(p, t, acc);
+            }
+        }
+        W[i] = acc;
+    }
+    if (Winv == nullptr) return;
+    // W^-1 = U'^-1 L'^-1 P^T.  Thread j solves W x = e_j: forward then backward substitution, all in fp64,
+    // rounded to fp32 once.  Replaces the per-pixel lu_solve of modules.py:490 by one matrix apply.
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+        double y[kMaxInvconvC];
+        for (int i = 0; i < C; ++i) {
+            double acc = static_cast<double>(__ldg(P + j * C + i));  // (P^T e_j)_i = P[j,i]
+            for (int k = 0; k < i; ++k) acc -= static_cast<double>(__ldg(L + i * C + k)) * y[k];
+            y[i] = acc;
+        }
+        for (int i = C - 1; i >= 0; --i) {
+            double acc = y[i];
+            for (int k = i + 1; k < C; ++k) acc -= static_cast<double>(__ldg(U + i * C + k)) * y[k];
+            y[i] = acc / static_cast<double>(diag[i]);
+        }
+        for (int i = 0; i < C; ++i) Winv[i * C + j] = static_cast<float>(y[i]);
+    }
+}
+
+// ---- apply: generic scalar kernel (any C, any HW; used for the 1-D case HW == 1 and odd shapes) ----------
+__global__ void __launch_bounds__(256) invconv_apply_scalar(const float* __restrict__ zin, float* __restrict__ zout,
+                                                           const float* ldj_in, float* ldj_out,
+                                                           const float* __restrict__ M, const float* __restrict__ log_s,
+                                                           float sign, int B, int C, int HW) {
+    if (static_cast<long long>(blockIdx.x) * blockDim.x < B) {
+        float part = 0.f;
+        for (int c = threadIdx.x & 31; c < C; c += 32) part += __ldg(log_s + c);
+        part = warp_sum(part);
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b < B) ldj_out[b] = __fadd_rn(ldj_in[b], __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+    }
+    const long long total = static_cast<long long>(B) * C * HW;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / (static_cast<long long>(C) * HW);
+        const int r = static_cast<int>(i - b * C * HW);
+        const int co = r / HW, p = r - co * HW;
+        const float* zb = zin + b * C * HW + p;
+        float acc = 0.f;
+        for (int ci = 0; ci < C; ++ci) acc = fmaf(__ldg(M + co * C + ci), __ldg(zb + static_cast<size_t>(ci) * HW), acc);
+        zout[i] = acc;
+    }
+}
+
+// ---- apply: tiled kernel.  CTA = one sample x TP pixels; thread = 4 pixels x OCG output channels ----------
+// shared: Mt[ci][co] (transposed so OCG consecutive co are one vector load), zs[ci][TP]
+template <int OCG>
+__global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restrict__ zin, float* __restrict__ zout,
+                                                          const float* ldj_in, float* ldj_out,
+                                                          const float* __restrict__ M, const float* __restrict__ log_s,
+                                                          float sign, int B, int C, int HW, int TP) {
+    extern __shared__ __align__(16) float sm[];
+    float* Mt = sm;                          // C*C
+    float* zs = sm + ((C * C + 3) & ~3);     // C*TP, 16-byte aligned
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * TP;
+    const int tp = (HW - p0) < TP ? (HW - p0) : TP;  // multiple of 4
+
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int co = i / C, ci = i - co * C;
+        Mt[ci * C + co] = __ldg(M + i);
+    }
+    const float* zb = zin + (static_cast<size_t>(b) * C) * HW + p0;
+    const int tpv = tp >> 2;
+    for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
+        const int ci = i / tpv, pv = i - ci * tpv;
+        st4(zs + ci * TP + 4 * pv, ldg4(zb + static_cast<size_t>(ci) * HW + 4 * pv));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        float part = 0.f;
+        for (int c = threadIdx.x; c < C; c += 32) part += __ldg(log_s + c);
+        part = warp_sum(part);
+        if (threadIdx.x == 0) ldj_out[b] = __fadd_rn(ldj_in[b], __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+    }
+    __syncthreads();
+
+    const int nog = C / OCG;
+    for (int w = threadIdx.x; w < nog * tpv; w += blockDim.x) {
+        const int og = w / tpv, pv = w - og * tpv;  // consecutive threads -> consecutive pixels, same og (broadcast)
+        float acc[OCG][4];
+#pragma unroll
+        for (int o = 0; o < OCG; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
+        const float* mrow = Mt + og * OCG;
+        const float* zcol = zs + 4 * pv;
+#pragma unroll 4
+        for (int ci = 0; ci < C; ++ci) {
+            const float4 z = ld4(zcol + ci * TP);
+            float m[OCG];
+#pragma unroll
+            for (int o = 0; o < OCG; ++o) m[o] = mrow[ci * C + o];
+#pragma unroll
+            for (int o = 0; o < OCG; ++o) {
+                acc[o][0] = fmaf(m[o], z.x, acc[o][0]);
+                acc[o][1] = fmaf(m[o], z.y, acc[o][1]);
+                acc[o][2] = fmaf(m[o], z.z, acc[o][2]);
+                acc[o][3] = fmaf(m[o], z.w, acc[o][3]);
+            }
+        }
+        float* ob = zout + (static_cast<size_t>(b) * C + og * OCG) * HW + p0 + 4 * pv;
+#pragma unroll
+        for (int o = 0; o < OCG; ++o) st4(ob + static_cast<size_t>(o) * HW, make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
+    }
+}
+
+template <int OCG>
+static int launch_tiled(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
+                        const float* log_s, float sign, int B, int C, int HW, cudaStream_t st) {
+    // pixel tile: whole sample if it fits, else the largest multiple of 4 that keeps shared memory <= ~96 KB
+    int TP = HW;
+    const size_t budget = 96 * 1024;
+    const size_t mt = (static_cast<size_t>(C) * C + 3) & ~static_cast<size_t>(3);
+    while ((mt + static_cast<size_t>(C) * TP) * 4 > budget && TP > 16) TP = ((TP / 2 + 3) / 4) * 4;
+    const size_t smem = (mt + static_cast<size_t>(C) * TP) * 4;
+    if (smem > 200 * 1024) return -100;  // caller falls back to the scalar kernel
+    auto kern = invconv_apply_tiled<OCG>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const int work = (C / OCG) * (TP / 4);
+    int threads = work >= 512 ? 512 : ((work + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    dim3 grid((HW + TP - 1) / TP, B);
+    kern<<<grid, threads, smem, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, sign, B, C, HW, TP);
+    return launch_status();
+}
+
+}  // namespace nfb
+
+using namespace nfb;
+
+extern "C" int nfb_invconv1x1_weight(const float* P, const float* L, const float* U, const float* log_s,
+                                     const float* sign_s, float* W_out, float* Winv_out, int C, nfb_stream_t stream) {
+    if (!P || !L || !U || !log_s || !sign_s || !W_out) return NFB_ERR_NULL;
+    if (C <= 0) return NFB_ERR_SHAPE;
+    if (C > kMaxInvconvC) return NFB_ERR_UNSUPPORTED;
+    invconv_weight_kernel<<<1, 256, 0, as_stream(stream)>>>(P, L, U, log_s, sign_s, W_out, Winv_out, C);
+    return launch_status();
+}
+
+extern "C" int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out,
+                                    const float* M, const float* log_s, float sign, int B, int C, int HW,
+                                    nfb_stream_t stream) {
+    if (!z_in || !z_out || !ldj_in || !ldj_out || !M || !log_s) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && B <= 65535) {
+        int rc = -100;
+        if (C % 8 == 0) rc = launch_tiled<8>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
+        else if (C % 4 == 0) rc = launch_tiled<4>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
+        else if (C % 3 == 0) rc = launch_tiled<3>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
+        else if (C % 2 == 0) rc = launch_tiled<2>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
+        else rc = launch_tiled<1>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
+        if (rc != -100) return rc;
+    }
+    const long long total = static_cast<long long>(B) * C * HW;
+    long long blocks = (total + 255) / 256;
+    const long long need = (B + 255) / 256;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    if (blocks < need) blocks = need;
+    invconv_apply_scalar<<<static_cast<int>(blocks), 256, 0, st>>>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW);
+    return launch_status();
+}

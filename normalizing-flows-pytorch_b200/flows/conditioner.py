@@ -1,0 +1,132 @@
+"""Conditioner networks of the couplings (modules.py:342-438, 500-578), same state_dict keys as the reference.
+
+``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
+-> out_block (BN, ReLU, WN-layer).  Eval mode only (running statistics).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib as L
+from .weight_norm import WeightNorm
+
+# The bits/dim parity bar (1e-5 relative, reference noise floor 2e-7) rules out TF32.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+class _ResBlock(nn.Module):
+    """parameter layout of ResBlockLinear / ResBlock2d (modules.py:342-388); `bridge` is empty (in == out)."""
+
+    def __init__(self, ch, conv):
+        super().__init__()
+        bn = nn.BatchNorm2d if conv else nn.BatchNorm1d
+        mk = (lambda: nn.Conv2d(ch, ch, 3, 1, 1)) if conv else (lambda: nn.Linear(ch, ch))
+        self.net = nn.Sequential(bn(ch), nn.ReLU(inplace=True), WeightNorm(mk()), bn(ch), nn.ReLU(inplace=True),
+                                 WeightNorm(mk()))
+        self.bridge = nn.Sequential()
+
+
+class _ResNetConditioner(nn.Module):
+    conv = False
+
+    def __init__(self, in_channels, out_channels, base_filters=32, n_blocks=2, weight_norm=True):
+        super().__init__()
+        if not weight_norm:
+            raise NotImplementedError('nfb200 conditioners are weight-normalised like every use in the reference')
+        self.in_channels, self.out_channels, self.base_filters = in_channels, out_channels, base_filters
+        if self.conv:
+            first, last = nn.Conv2d(in_channels, base_filters, 3, 1, 1), nn.Conv2d(base_filters, out_channels, 1, 1, 0)
+            bn = nn.BatchNorm2d
+        else:
+            first, last = nn.Linear(in_channels, base_filters), nn.Linear(base_filters, out_channels)
+            bn = nn.BatchNorm1d
+        self.in_block = nn.Sequential(WeightNorm(first))
+        self.mid_block = nn.Sequential(*[_ResBlock(base_filters, self.conv) for _ in range(n_blocks)])
+        self.out_block = nn.Sequential(bn(base_filters), nn.ReLU(inplace=True), WeightNorm(last))
+
+    # -- building blocks of the eval-mode forward -------------------------------------------------------
+    def _layer(self, wn, x):
+        w = wn.weight()
+        if self.conv:
+            return F.conv2d(x, w, wn.bias, 1, (w.size(2) - 1) // 2)
+        return F.linear(x, w, wn.bias)
+
+    @staticmethod
+    def _bn_relu(bn, x):
+        return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
+
+    def forward(self, x):
+        if self.training:
+            raise RuntimeError('nfb200 conditioners implement the eval-mode (running statistics) path only')
+        x = L.dev(x, 'conditioner input')
+        with torch.no_grad():
+            x = self._layer(self.in_block[0], x)
+            for blk in self.mid_block:
+                y = self._bn_relu(blk.net[0], x)
+                y = self._layer(blk.net[2], y)
+                y = self._bn_relu(blk.net[3], y)
+                y = self._layer(blk.net[5], y)
+                x = x + y
+            x = self._bn_relu(self.out_block[0], x)
+            return self._layer(self.out_block[2], x)
+
+
+class MLP(_ResNetConditioner):
+    """modules.py:391-413."""
+    conv = False
+
+
+class ConvNet(_ResNetConditioner):
+    """modules.py:416-438."""
+    conv = True
+
+
+# ---- Flow++ conditioner pieces (modules.py:500-578) -- torch ops on the device for now ----
+
+
+class GatedLinear(nn.Module):
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.op = nn.Linear(in_features * 2, out_features)
+
+    def forward(self, x):
+        C = x.size(1)
+        y = self.op(F.elu(torch.cat([x, -x], dim=1)))
+        y = F.elu(torch.cat([y, -y], dim=1))
+        return x + y[:, :C] * torch.sigmoid(y[:, C:])
+
+
+class GatedConv2d(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.op = nn.Conv2d(in_channels * 2, out_channels, 3, 1, 1)
+
+    def forward(self, x):
+        C = x.size(1)
+        y = self.op(F.elu(torch.cat([x, -x], dim=1)))
+        y = F.elu(torch.cat([y, -y], dim=1))
+        return x + y[:, :C] * torch.sigmoid(y[:, C:])
+
+
+class GatedAttn(nn.Module):
+    def __init__(self, in_out_shape, filters=8, heads=4):
+        super().__init__()
+        assert filters % heads == 0
+        self.channels, self.filters, self.heads = in_out_shape[0], filters, heads
+        self.conv1 = nn.Conv1d(self.channels, filters * 3, 1, 1, 0)
+        self.conv2 = nn.Conv1d(filters, self.channels * 2, 1, 1, 0)
+        self.pos_emb = nn.Parameter(torch.randn(1, *in_out_shape) * 0.01)
+
+    def forward(self, x):
+        shape = x.size()
+        B, C = shape[0], shape[1]
+        D = self.filters // self.heads
+        p = self.conv1((x + self.pos_emb).view(B, C, -1)).view(B, 3 * self.heads, D, -1)
+        V, K, Q = torch.split(p, self.heads, dim=1)  # order of modules.py:566
+        Wm = F.softmax(torch.matmul(V.permute(0, 1, 3, 2), K) / np.sqrt(D), dim=2)
+        A = torch.matmul(Q, Wm).view(B, C, -1)
+        y = self.conv2(A)
+        y = (y[:, :C] * torch.sigmoid(y[:, C:])).view(shape)
+        return x + y

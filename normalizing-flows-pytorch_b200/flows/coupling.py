@@ -1,0 +1,168 @@
+"""Coupling layers of the reference's ``flows/coupling.py`` with the bijection, the split-gather / merge-scatter
+and the per-sample log-det fused into one libnfb200 kernel each.
+
+Only the conditioner input z1 is materialised (one gather); z0, (t, s), the merged output and the log-det never
+exist as separate tensors.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .conditioner import MLP, ConvNet, GatedAttn, GatedConv2d, GatedLinear
+from .squeeze import coupling_split
+
+
+class AbstractCoupling(nn.Module):
+    """coupling.py:12-49: chooses the split from (len(dims), masking)."""
+
+    def __init__(self, dims, masking='checkerboard', odd=False):
+        super().__init__()
+        self.dims = tuple(dims)
+        self.odd = bool(odd)
+        if len(dims) == 1:
+            self.mode = L.SPLIT_1D
+        elif len(dims) == 3 and masking == 'checkerboard':
+            self.mode = L.SPLIT_CHECKER
+        elif len(dims) == 3 and masking == 'channelwise':
+            self.mode = L.SPLIT_CHANNEL
+        else:
+            raise Exception('unsupported combination of masking and dimension: %s, %s' % (masking, str(dims)))
+
+    def _half_channels(self):
+        """(in_chs of the conditioner, channels of the transformed half) -- coupling.py:92-101."""
+        d = self.dims
+        if len(d) == 1:
+            in_chs = d[0] // 2 if not self.odd else (d[0] + 1) // 2
+            return in_chs, d[0] - in_chs
+        c = d[0] * 2 if self.mode == L.SPLIT_CHECKER else d[0] // 2
+        return c, c
+
+    def _geom(self, z):
+        if z.dim() == 2:
+            return z.size(0), z.size(1), 1, 1
+        return tuple(z.shape)
+
+    def _params(self, z):
+        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
+        return L.dev(self.net(z1), 'conditioner output')
+
+    def forward(self, z, log_df_dz):
+        return self._run(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), False)
+
+    def backward(self, y, log_df_dz):
+        return self._run(L.dev(y, 'y'), L.dev(log_df_dz, 'log_df_dz'), True)
+
+    inverse = backward
+
+
+class AdditiveCoupling(AbstractCoupling):
+    """coupling.py:52-79 (NICE); no log-det."""
+
+    def __init__(self, dims, masking='checkerboard', odd=False):
+        super().__init__(dims, masking, odd)
+        in_chs, out_chs = self._half_channels()
+        self.net_t = MLP(in_chs, out_chs) if len(dims) == 1 else ConvNet(in_chs, out_chs)
+
+    def _params(self, z):
+        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
+        return L.dev(self.net_t(z1), 'conditioner output')
+
+    def _run(self, z, ldj, inverse):
+        B, C, H, W = self._geom(z)
+        t = self._params(z)
+        out = torch.empty_like(z)
+        L.check(L.lib().nfb_additive_coupling(L.ptr(z), L.ptr(out), L.ptr(t), -1.0 if inverse else 1.0, B, C, H, W,
+                                              self.mode, int(self.odd), L.stream()))
+        return out, ldj
+
+
+class AffineCoupling(AbstractCoupling):
+    """coupling.py:82-122 (RealNVP / Glow)."""
+
+    def __init__(self, dims, masking='checkerboard', odd=False):
+        super().__init__(dims, masking, odd)
+        self.s_log_scale = nn.Parameter(torch.randn(1) * 0.01)
+        self.s_bias = nn.Parameter(torch.randn(1) * 0.01)
+        in_chs, self.out_chs = self._half_channels()
+        self.net = MLP(in_chs, self.out_chs * 2) if len(dims) == 1 else ConvNet(in_chs, self.out_chs * 2)
+
+    def _run(self, z, ldj, inverse):
+        B, C, H, W = self._geom(z)
+        params = self._params(z)
+        out = torch.empty_like(z)
+        fn = L.lib().nfb_affine_coupling_inv if inverse else L.lib().nfb_affine_coupling_fwd
+        L.check(fn(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj), L.ptr(self.s_log_scale.data),
+                   L.ptr(self.s_bias.data), B, C, H, W, self.mode, int(self.odd), L.stream()))
+        return out, ldj
+
+
+class MixLogAttnCoupling(AbstractCoupling):
+    """coupling.py:125-210 (Flow++): logistic-mixture CDF -> logit -> affine."""
+
+    def __init__(self, dims, masking='checkerboard', odd=False, base_filters=32, n_mixtures=4):
+        super().__init__(dims, masking, odd)
+        self.n_mixtures = n_mixtures
+        self.a_log_scale = nn.Parameter(torch.randn(1) * 0.01)
+        self.a_bias = nn.Parameter(torch.randn(1) * 0.01)
+        in_chs, out_chs = self._half_channels()
+        self.sections = [out_chs] * 2 + [out_chs * n_mixtures] * 3
+        if len(dims) == 1:
+            mid_shape = (base_filters, )
+            self.net = nn.Sequential(nn.Linear(in_chs, base_filters), GatedLinear(base_filters, base_filters),
+                                     nn.LayerNorm(mid_shape), GatedAttn(mid_shape, base_filters),
+                                     nn.LayerNorm(mid_shape), nn.Linear(base_filters, sum(self.sections)))
+        else:
+            sp = tuple(d // 2 for d in dims[1:]) if self.mode == L.SPLIT_CHECKER else tuple(dims[1:])
+            mid_shape = (base_filters, ) + sp
+            self.net = nn.Sequential(nn.Conv2d(in_chs, base_filters, 3, 1, 1), GatedConv2d(base_filters, base_filters),
+                                     nn.LayerNorm(mid_shape), GatedAttn(mid_shape, base_filters),
+                                     nn.LayerNorm(mid_shape), nn.Conv2d(base_filters, sum(self.sections), 3, 1, 1))
+        self._scratch = None
+        self._flag = None
+
+    def _params(self, z):
+        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
+        with torch.no_grad():
+            return L.dev(self.net(z1), 'conditioner output')
+
+    def _run(self, z, ldj, inverse):
+        B, C, H, W = self._geom(z)
+        params = self._params(z)
+        out = torch.empty_like(z)
+        ldj_out = torch.empty_like(ldj)  # MixLogCDF / Logit return new log-det tensors (modules.py:194,150)
+        if not inverse:
+            L.check(L.lib().nfb_mixlog_coupling_fwd(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj_out),
+                                                    L.ptr(self.a_log_scale.data), L.ptr(self.a_bias.data), B, C, H, W,
+                                                    self.mode, int(self.odd), self.n_mixtures, L.stream()))
+            return out, ldj_out
+        n = z.numel()  # 2 floats (lo, hi) per transformed element
+        if self._scratch is None or self._scratch.numel() < n or self._scratch.device != z.device:
+            self._scratch = torch.empty(n, device=z.device, dtype=torch.float32)
+            self._flag = torch.zeros(1, device=z.device, dtype=torch.int32)
+        L.check(L.lib().nfb_mixlog_coupling_inv(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj_out),
+                                                L.ptr(self.a_log_scale.data), L.ptr(self.a_bias.data),
+                                                L.ptr(self._scratch), L.ptr(self._flag), B, C, H, W, self.mode,
+                                                int(self.odd), self.n_mixtures, L.stream()))
+        return out, ldj_out
+
+
+class RQSplineCoupling(AbstractCoupling):
+    """Rational-quadratic spline coupling (Durkan et al. 2019) inside the reference's coupling container
+    (coupling.py:12-49).  Not present in the reference; conditioner = the reference's MLP / ConvNet
+    emitting (3K-1) values per transformed feature, bin-major."""
+
+    def __init__(self, dims, masking='checkerboard', odd=False, n_bins=8, tail_bound=3.0):
+        super().__init__(dims, masking, odd)
+        self.n_bins, self.tail_bound = n_bins, float(tail_bound)
+        in_chs, out_chs = self._half_channels()
+        n_out = out_chs * (3 * n_bins - 1)
+        self.net = MLP(in_chs, n_out) if len(dims) == 1 else ConvNet(in_chs, n_out)
+
+    def _run(self, z, ldj, inverse):
+        B, C, H, W = self._geom(z)
+        params = self._params(z)
+        out = torch.empty_like(z)
+        fn = L.lib().nfb_rqs_coupling_inv if inverse else L.lib().nfb_rqs_coupling_fwd
+        L.check(fn(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj), B, C, H, W, self.mode, int(self.odd),
+                   self.n_bins, self.tail_bound, L.stream()))
+        return out, ldj

@@ -1,0 +1,215 @@
+"""Bijective layers of the reference's ``flows/modules.py`` on libnfb200 (CUDA, sm_100a).
+
+Same class names, constructor signatures, ``forward(z, log_df_dz)`` / ``backward(y, log_df_dz)`` methods and
+``state_dict`` keys as the reference, so reference checkpoints load unchanged.  ``inverse`` is an
+alias of ``backward``.  Inference only: the kernels have no autograd.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+
+def _bchw(z):
+    if z.dim() == 2:
+        return z.size(0), z.size(1), 1
+    return z.size(0), z.size(1), z[0, 0].numel()
+
+
+class Logit(nn.Module):
+    """modules.py:141-155.  Returns a NEW log-det tensor like the reference."""
+
+    def __init__(self, eps=1.0e-5):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x, log_df_dz):
+        x, log_df_dz = L.dev(x, 'x'), L.dev(log_df_dz, 'log_df_dz')
+        out, ldj = torch.empty_like(x), torch.empty_like(log_df_dz)
+        B = x.size(0)
+        # torch.clamp(x, eps, 1.0 - eps) rounds the python doubles to fp32 (modules.py:147)
+        lo, hi = float(np.float32(self.eps)), float(np.float32(1.0 - self.eps))
+        L.check(L.lib().nfb_logit_fwd(L.ptr(x), L.ptr(out), L.ptr(log_df_dz), L.ptr(ldj), lo, hi, B, x[0].numel(),
+                                      L.stream()))
+        return out, ldj
+
+    def backward(self, x, log_df_dz):
+        x, log_df_dz = L.dev(x, 'x'), L.dev(log_df_dz, 'log_df_dz')
+        out, ldj = torch.empty_like(x), torch.empty_like(log_df_dz)
+        L.check(L.lib().nfb_logit_inv(L.ptr(x), L.ptr(out), L.ptr(log_df_dz), L.ptr(ldj), x.size(0), x[0].numel(),
+                                      L.stream()))
+        return out, ldj
+
+    inverse = backward
+
+
+class ActNorm(nn.Module):
+    """modules.py:225-256 (data-dependent init on the first call; ``initialized`` is a plain attribute)."""
+
+    def __init__(self, num_features, eps=1.0e-5):
+        super().__init__()
+        self.num_features = num_features
+        self.eps = eps
+        self.dimensions = [1] + [1 for _ in num_features]
+        self.dimensions[1] = num_features[0]
+        self.log_scale = nn.Parameter(torch.zeros(self.dimensions))
+        self.bias = nn.Parameter(torch.zeros(self.dimensions))
+        self.initialized = False
+
+    def forward(self, z, log_df_dz):
+        z, log_df_dz = L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz')
+        B, C, HW = _bchw(z)
+        if not self.initialized:
+            L.check(L.lib().nfb_actnorm_init(L.ptr(z), L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW,
+                                             float(self.eps), L.stream()))
+            self.initialized = True
+        out = torch.empty_like(z)
+        L.check(L.lib().nfb_actnorm_fwd(L.ptr(z), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz),
+                                        L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW, L.stream()))
+        return out, log_df_dz
+
+    def backward(self, y, log_df_dz):
+        y, log_df_dz = L.dev(y, 'y'), L.dev(log_df_dz, 'log_df_dz')
+        B, C, HW = _bchw(y)
+        out = torch.empty_like(y)
+        L.check(L.lib().nfb_actnorm_inv(L.ptr(y), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz),
+                                        L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW, L.stream()))
+        return out, log_df_dz
+
+    inverse = backward
+
+
+class BatchNorm(nn.Module):
+    """flow BatchNorm, modules.py:259-322 (train mode: batch statistics + running-stat update)."""
+
+    def __init__(self, num_features, momentum=0.1, eps=1.0e-5, affine=True):
+        super().__init__()
+        self.num_features = num_features
+        self.eps = eps
+        self.momentum = momentum
+        self.dimensions = [1] + [1 for _ in num_features]
+        self.dimensions[1] = num_features[0]
+        if affine:
+            self.log_gamma = nn.Parameter(torch.zeros(self.dimensions))
+            self.beta = nn.Parameter(torch.zeros(self.dimensions))
+        else:
+            self.register_buffer('log_gamma', torch.zeros(self.dimensions))
+            self.register_buffer('beta', torch.zeros(self.dimensions))
+        self.register_buffer('running_mean', torch.zeros(self.dimensions))
+        self.register_buffer('running_var', torch.ones(self.dimensions))
+        self.register_buffer('batch_mean', torch.zeros(self.dimensions))
+        self.register_buffer('batch_var', torch.ones(self.dimensions))
+
+    def _stats(self):
+        if self.training:
+            return self.batch_mean, self.batch_var
+        return self.running_mean, self.running_var
+
+    def forward(self, x, log_det_jacob):
+        x, log_det_jacob = L.dev(x, 'x'), L.dev(log_det_jacob, 'log_det_jacob')
+        B, C, HW = _bchw(x)
+        if self.training:
+            L.check(L.lib().nfb_bnflow_batch_stats(L.ptr(x), L.ptr(self.batch_mean), L.ptr(self.batch_var), B, C, HW,
+                                                   float(self.eps), L.stream()))
+            with torch.no_grad():  # modules.py:291-294 (C-element bookkeeping)
+                self.running_mean.mul_(1.0 - self.momentum).add_(self.batch_mean * self.momentum)
+                self.running_var.mul_(1.0 - self.momentum).add_(self.batch_var * self.momentum)
+        mean, var = self._stats()
+        out = torch.empty_like(x)
+        L.check(L.lib().nfb_bnflow_fwd(L.ptr(x), L.ptr(out), L.ptr(log_det_jacob), L.ptr(log_det_jacob), L.ptr(mean),
+                                       L.ptr(var), L.ptr(self.log_gamma.data), L.ptr(self.beta.data), B, C, HW,
+                                       L.stream()))
+        return out, log_det_jacob
+
+    def backward(self, x, log_det_jacob):
+        x, log_det_jacob = L.dev(x, 'x'), L.dev(log_det_jacob, 'log_det_jacob')
+        B, C, HW = _bchw(x)
+        mean, var = self._stats()
+        out = torch.empty_like(x)
+        L.check(L.lib().nfb_bnflow_inv(L.ptr(x), L.ptr(out), L.ptr(log_det_jacob), L.ptr(log_det_jacob), L.ptr(mean),
+                                       L.ptr(var), L.ptr(self.log_gamma.data), L.ptr(self.beta.data), B, C, HW,
+                                       L.stream()))
+        return out, log_det_jacob
+
+    inverse = backward
+
+
+class InvertibleConv1x1(nn.Module):
+    """modules.py:441-497.  W = P L U is assembled (and inverted, fp64 on the device) by one small kernel and
+    cached until L / U / log_s change, instead of two matmuls per forward and an lu_solve per inverse."""
+
+    def __init__(self, in_out_channels):
+        super().__init__()
+        C = in_out_channels
+        W = torch.zeros((C, C), dtype=torch.float32)
+        nn.init.orthogonal_(W)
+        LU, pivots = torch.linalg.lu_factor(W)
+        P, Lo, Up = torch.lu_unpack(LU, pivots)
+        self.P = nn.Parameter(P, requires_grad=False)
+        self.L = nn.Parameter(Lo, requires_grad=True)
+        self.U = nn.Parameter(Up, requires_grad=True)
+        self.I = nn.Parameter(torch.eye(C), requires_grad=False)
+        self.pivots = nn.Parameter(pivots, requires_grad=False)
+        self.L_mask = nn.Parameter(torch.tril(torch.ones(C, C), -1), requires_grad=False)
+        self.U_mask = nn.Parameter(torch.triu(torch.ones(C, C), 1), requires_grad=False)
+        s = torch.diag(Up)
+        self.log_s = nn.Parameter(torch.log(torch.abs(s)), requires_grad=True)
+        self.sign_s = nn.Parameter(torch.sign(s), requires_grad=False)
+        self._cache_key = None
+        self._W = None
+        self._Winv = None
+
+    def matrices(self):
+        """(W, W^-1) device tensors, rebuilt only when a parameter changed."""
+        ps = (self.P, self.L, self.U, self.log_s, self.sign_s)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._cache_key:
+            C = self.L.size(0)
+            dev = self.L.device
+            if self._W is None or self._W.device != dev:
+                self._W = torch.empty((C, C), device=dev, dtype=torch.float32)
+                self._Winv = torch.empty((C, C), device=dev, dtype=torch.float32)
+            for p in ps:
+                L.dev(p.data, 'InvertibleConv1x1 parameter')
+            L.check(L.lib().nfb_invconv1x1_weight(L.ptr(self.P.data), L.ptr(self.L.data), L.ptr(self.U.data),
+                                                  L.ptr(self.log_s.data), L.ptr(self.sign_s.data), L.ptr(self._W),
+                                                  L.ptr(self._Winv), C, L.stream()))
+            self._cache_key = key
+        return self._W, self._Winv
+
+    def _apply_matrix(self, z, log_df_dz, M, sign):
+        z, log_df_dz = L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz')
+        B, C, HW = _bchw(z)
+        out = torch.empty_like(z)
+        L.check(L.lib().nfb_invconv1x1_apply(L.ptr(z), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz), L.ptr(M),
+                                             L.ptr(self.log_s.data), float(sign), B, C, HW, L.stream()))
+        return out, log_df_dz
+
+    def forward(self, z, log_df_dz):
+        return self._apply_matrix(z, log_df_dz, self.matrices()[0], 1.0)
+
+    def backward(self, y, log_df_dz):
+        return self._apply_matrix(y, log_df_dz, self.matrices()[1], -1.0)
+
+    inverse = backward
+
+
+class Compose(nn.Module):
+    """modules.py:325-339: sequential / reversed application."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, z, log_df_dz):
+        for layer in self.layers:
+            z, log_df_dz = layer(z, log_df_dz)
+        return z, log_df_dz
+
+    def backward(self, z, log_df_dz):
+        for layer in reversed(self.layers):
+            z, log_df_dz = layer.backward(z, log_df_dz)
+        return z, log_df_dz
+
+    inverse = backward

@@ -1,0 +1,318 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path through the C ABI against the CPU
+oracle and against the committed golden vectors from the reference.
+
+Tolerances: index permutations bit-exact (torch.equal); floating point: elementwise outputs 1e-5 (abs+rel; libdevice
+vs Sleef transcendentals differ by ~1-2 ulp and go through exp), per-sample log-det 1e-5 relative; bits/dim 1e-5
+relative (BASELINE.json north_star) -- in practice ~1e-7.
+"""
+import math
+import types
+
+import pytest
+import torch
+
+from tests import _golden
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def nfb():
+    import nfb200
+    return nfb200
+
+
+def close(a, b, rtol=1e-5, atol=1e-5, what=''):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    assert bool((err <= tol).all()), '%s max err %.3e (tol %.1e/%.1e)' % (what, float(err.max()), rtol, atol)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# permutations: bit exact
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(2, 1, 2, 2), (2, 3, 4, 4), (3, 2, 6, 4), (2, 12, 8, 8), (2, 3, 32, 32),
+                                   (1, 48, 8, 8), (2, 6, 16, 24)])
+@pytest.mark.parametrize('odd', [False, True])
+def test_permutations_bit_exact(shape, odd):
+    F = nfb().flows
+    z = torch.randn(shape)
+    zg = z.to(DEV)
+    z0, z1 = F.checker_split(zg, odd)
+    o0, o1 = O.checker_split(z, odd)
+    assert torch.equal(z0.cpu(), o0) and torch.equal(z1.cpu(), o1)
+    assert torch.equal(F.checker_merge(z0, z1, odd).cpu(), z)
+    if shape[1] % 2 == 0:
+        c0, c1 = F.channel_split(zg, 1, odd)
+        p0, p1 = O.channel_split(z, odd)
+        assert torch.equal(c0.cpu(), p0) and torch.equal(c1.cpu(), p1)
+        assert torch.equal(F.channel_merge(c0, c1, 1, odd).cpu(), z)
+    sq = F.Squeeze2d(odd)(zg, None)[0]
+    assert torch.equal(sq.cpu(), O.squeeze2d_layer(z, odd))
+    assert torch.equal(F.Unsqueeze2d(odd)(sq, None)[0].cpu(), z)
+    assert torch.equal(F.Squeeze2d(odd).backward(sq, None)[0].cpu(), z)
+
+
+@pytest.mark.parametrize('C', [2, 10, 64])
+@pytest.mark.parametrize('odd', [False, True])
+def test_split1d_bit_exact(C, odd):
+    F = nfb().flows
+    z = torch.randn(5, C)
+    a, b = F.squeeze1d(z.to(DEV), odd)
+    oa, ob = O.split1d(z, odd)
+    assert torch.equal(a.cpu(), oa) and torch.equal(b.cpu(), ob)
+    assert torch.equal(F.unsqueeze1d(a, b, odd).cpu(), z)
+
+
+def test_permutations_golden():
+    F = nfb().flows
+    _, a, _ = _golden.load('permutations')
+    for tag in ('1x2x2', '3x4x4', '2x6x4', '12x8x8'):
+        z = a['in_' + tag].to(DEV)
+        for odd in (0, 1):
+            z0, z1 = F.checker_split(z, bool(odd))
+            assert torch.equal(z0.cpu(), a['checker_%s_%d_z0' % (tag, odd)])
+            assert torch.equal(z1.cpu(), a['checker_%s_%d_z1' % (tag, odd)])
+            assert torch.equal(F.Squeeze2d(bool(odd))(z, None)[0].cpu(), a['squeeze2d_%s_%d' % (tag, odd)])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single layers vs golden vectors from the reference
+# ---------------------------------------------------------------------------------------------------------
+def build_layer(meta):
+    F = nfb().flows
+    kind, kw = meta['kind'], dict(meta['kwargs'])
+    for k in ('dims', 'num_features'):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    layer = getattr(F, kind)(**kw)
+    return layer
+
+
+LAYER_CASES = [n for n in _golden.names() if not n.startswith(('model_', 'permutations', 'stats_'))]
+
+
+@pytest.mark.parametrize('name', LAYER_CASES)
+def test_layer_vs_reference_golden(name):
+    meta, a, sd = _golden.load(name)
+    layer = build_layer(meta)
+    layer.load_state_dict(sd)
+    if hasattr(layer, 'initialized'):
+        layer.initialized = True
+    layer.to(DEV).eval()
+    z, ldj = layer(a['x'].to(DEV), a['ldj0'].to(DEV).clone())
+    close(z, a['fwd_z'], what=name + ' fwd z')
+    close(ldj, a['fwd_ldj'], rtol=1e-5, atol=2e-5, what=name + ' fwd ldj')
+    y, ldj2 = layer.backward(a['fwd_z'].to(DEV), a['ldj0'].to(DEV).clone())
+    tol = 2e-4 if meta['kind'] == 'MixLogAttnCoupling' else 3e-5 if meta['kind'] == 'InvertibleConv1x1' else 1e-5
+    close(y, a['inv_y'], rtol=tol, atol=tol, what=name + ' inv y')
+    close(ldj2, a['inv_ldj'], rtol=max(tol, 1e-5), atol=20 * tol, what=name + ' inv ldj')
+
+
+def test_stats_paths_vs_golden():
+    F = nfb().flows
+    _, a, _ = _golden.load('stats_init')
+    x = a['x'].to(DEV)
+    an = F.ActNorm((12, 4, 4)).to(DEV)
+    z, l = an(x, torch.zeros(6, device=DEV))
+    assert an.initialized
+    close(an.log_scale, a['an_log_scale'], what='actnorm init log_scale')
+    close(an.bias, a['an_bias'], what='actnorm init bias')
+    close(z, a['an_z'])
+    close(l, a['an_ldj'], atol=1e-4)
+    bn = F.BatchNorm((12, 4, 4), affine=False).to(DEV)
+    bn.train()
+    zb, lb = bn(x, torch.zeros(6, device=DEV))
+    close(bn.batch_mean, a['bn_batch_mean'])
+    close(bn.batch_var, a['bn_batch_var'])
+    close(bn.running_mean, a['bn_running_mean'])
+    close(bn.running_var, a['bn_running_var'])
+    close(zb, a['bn_z'])
+    close(lb, a['bn_ldj'], atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole stacks vs golden (reference) and vs oracle
+# ---------------------------------------------------------------------------------------------------------
+def build_model(meta, **extra):
+    n = nfb()
+    cls = {'RealNVP': n.RealNVP, 'Glow': n.Glow, 'Flowpp': n.Flowpp}[meta['kind']]
+    cfg = types.SimpleNamespace(layers=meta['layers'], mixtures=meta['mixtures'], **extra)
+    return cls(tuple(meta['dims']), meta['datatype'], cfg)
+
+
+@pytest.mark.parametrize('name', _golden.names('model_'))
+def test_model_vs_reference_golden(name):
+    meta, a, sd = _golden.load(name)
+    net = build_model(meta)
+    net.load_state_dict(sd)
+    net.mark_initialized().to(DEV).eval()
+    z, ldj = net(a['x'].to(DEV))
+    close(z, a['fwd_z'], rtol=5e-5, atol=5e-5, what=name + ' z')
+    close(ldj, a['fwd_ldj'], rtol=1e-5, atol=2e-4, what=name + ' ldj')
+    bpd = net.bits_per_dim(a['x'].to(DEV))
+    assert abs(bpd - meta['bpd']) <= 1e-5 * abs(meta['bpd']), (bpd, meta['bpd'])
+    if meta['kind'] != 'Flowpp':
+        y, ldj2 = net.backward(a['fwd_z'].to(DEV))
+        close(y, a['inv_y'], rtol=2e-4, atol=2e-4, what=name + ' inv y')
+        close(ldj2, a['inv_ldj'], rtol=1e-4, atol=2e-3, what=name + ' inv ldj')
+    else:  # bisection: compare against the input instead (reference round-trip error ~2e-5)
+        y, _ = net.backward(z)
+        # the leading Logit(0.01) clamps to [0.01, 0.99] (glow.py:20), so that is what the inverse can recover
+        close(y, a['x'].clamp(0.01, 0.99), rtol=5e-4, atol=5e-4, what=name + ' round trip')
+
+
+def oracle_spec(model, dims, datatype, layers, mixtures=4, coupling=None):
+    return O.stack_spec(model, dims, datatype, layers, mixtures, coupling)
+
+
+def perturb_(net, seed=0):
+    """Move BatchNorm/ActNorm/conv parameters away from their near-identity initial values (seeded)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, t in list(net.named_parameters()) + list(net.named_buffers()):
+            leaf = name.split('.')[-1]
+            if not t.is_floating_point() or leaf in ('P', 'I', 'L_mask', 'U_mask', 'sign_s', 'pivots'):
+                continue
+            if leaf in ('running_var', 'batch_var'):
+                t.copy_(0.5 + torch.rand(t.shape, generator=g))
+            elif leaf in ('running_mean', 'beta', 'bias', 'log_gamma', 'log_scale', 'L', 'U', 'log_s'):
+                t.add_(0.05 * torch.randn(t.shape, generator=g))
+            elif leaf in ('s_log_scale', 'a_log_scale'):
+                t.copy_(0.3 + 0.1 * torch.randn(t.shape, generator=g))
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(model='glow', dims=(3, 32, 32), datatype='image', layers=4, B=8),   # BASELINE cfg 2 stack at K=4
+    dict(model='glow', dims=(3, 64, 64), datatype='image', layers=2, B=2),   # cfg 5 stack (C up to 192) at K=2
+    dict(model='realnvp', dims=(64, ), datatype=None, layers=8, B=4096),      # cfg 4 proxy (affine)
+    dict(model='realnvp', dims=(2, ), datatype=None, layers=6, B=512),        # cfg 1
+    dict(model='flowpp', dims=(3, 32, 32), datatype='image', layers=1, B=2, mixtures=8),  # cfg 3 stack at K=1
+])
+def test_model_vs_oracle(cfg):
+    n = nfb()
+    torch.manual_seed(0)
+    cls = {'glow': n.Glow, 'realnvp': n.RealNVP, 'flowpp': n.Flowpp}[cfg['model']]
+    mixtures = cfg.get('mixtures', 4)
+    net = cls(cfg['dims'], cfg['datatype'], types.SimpleNamespace(layers=cfg['layers'], mixtures=mixtures))
+    perturb_(net)
+    net.mark_initialized().eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand((cfg['B'], ) + cfg['dims'], generator=gen) if cfg['datatype'] == 'image' else \
+        torch.randn((cfg['B'], ) + cfg['dims'], generator=gen)
+    spec = oracle_spec(cfg['model'], cfg['dims'], cfg['datatype'], cfg['layers'], mixtures)
+    with torch.no_grad():
+        zo, lo = O.stack_forward(spec, sd, x)
+    net.to(DEV)
+    z, ldj = net(x.to(DEV))
+    close(z, zo, rtol=1e-4, atol=1e-4, what='z')
+    close(ldj, lo, rtol=1e-5, atol=1e-3, what='ldj')
+    bo = O.bits_per_dim(zo, lo)
+    bg = net.bits_per_dim(x.to(DEV))
+    assert abs(bg - bo) <= 1e-5 * abs(bo), (bg, bo)
+    y, _ = net.backward(z)
+    xr = x.clamp(0.01, 0.99) if cfg['datatype'] == 'image' else x
+    close(y, xr, rtol=2e-3, atol=2e-3, what='round trip')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# RQ-spline coupling: no reference; oracle restatement of Durkan et al. in fp64
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dims,masking', [((64, ), 'checkerboard'), ((4, 8, 8), 'checkerboard'),
+                                          ((4, 8, 8), 'channelwise'), ((6, ), 'checkerboard')])
+@pytest.mark.parametrize('odd', [False, True])
+def test_rqs_coupling_vs_oracle(dims, masking, odd):
+    F = nfb().flows
+    torch.manual_seed(3)
+    layer = F.RQSplineCoupling(dims, masking=masking, odd=odd, n_bins=8, tail_bound=3.0)
+    perturb_(layer, 5)
+    layer.eval()
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    x = torch.randn((16, ) + dims, generator=torch.Generator().manual_seed(2)) * 2.0  # some mass in the tails
+    opt = dict(dims=dims, masking=masking, odd=odd, mixtures=4)
+    sd64 = O.to_dtype(sd, torch.float64)
+    with torch.no_grad():
+        zo, lo = O._coupling('rqs', opt, sd64, '', x.double(), torch.zeros(16, dtype=torch.float64), False)
+    layer.to(DEV)
+    z, ldj = layer(x.to(DEV), torch.zeros(16, device=DEV))
+    close(z, zo, rtol=2e-5, atol=2e-5, what='rqs fwd')
+    close(ldj, lo, rtol=2e-5, atol=2e-4, what='rqs ldj')
+    y, ldj2 = layer.backward(z, ldj.clone())
+    close(y, x, rtol=1e-4, atol=1e-4, what='rqs round trip')
+    close(ldj2, torch.zeros(16), atol=1e-3, what='rqs log-det cancels')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (no CPU oracle needed)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dims,masking,B', [((3, 32, 32), 'checkerboard', 256), ((12, 16, 16), 'channelwise', 256),
+                                            ((48, 8, 8), 'checkerboard', 256), ((64, ), 'checkerboard', 65536),
+                                            ((3, 64, 64), 'checkerboard', 64), ((192, 8, 8), 'channelwise', 64)])
+def test_affine_kernel_properties_full_size(dims, masking, B):
+    import nfb200._lib as L
+    mode = L.SPLIT_1D if len(dims) == 1 else (L.SPLIT_CHECKER if masking == 'checkerboard' else L.SPLIT_CHANNEL)
+    C, H, W = (dims + (1, 1))[:3] if len(dims) == 1 else dims
+    g = torch.Generator(device=DEV).manual_seed(0)
+    z = torch.randn((B, ) + dims, device=DEV, generator=g)
+    params = torch.randn((B, ) + dims, device=DEV, generator=g)  # (t | s_raw) has exactly D entries per sample
+    a = torch.tensor([0.3], device=DEV)
+    b = torch.tensor([-0.05], device=DEV)
+    for odd in (0, 1):
+        out = torch.empty_like(z)
+        ldj = torch.zeros(B, device=DEV)
+        L.check(L.lib().nfb_affine_coupling_fwd(z.data_ptr(), out.data_ptr(), params.data_ptr(), ldj.data_ptr(),
+                                                ldj.data_ptr(), a.data_ptr(), b.data_ptr(), B, C, H, W, mode, odd,
+                                                L.stream()))
+        # (1) in-place == out-of-place, bit for bit
+        z2 = z.clone()
+        ldj2 = torch.zeros(B, device=DEV)
+        L.check(L.lib().nfb_affine_coupling_fwd(z2.data_ptr(), z2.data_ptr(), params.data_ptr(), ldj2.data_ptr(),
+                                                ldj2.data_ptr(), a.data_ptr(), b.data_ptr(), B, C, H, W, mode, odd,
+                                                L.stream()))
+        assert torch.equal(out, z2) and torch.equal(ldj, ldj2)
+        # (2) the pass-through half is untouched bit for bit; the log-det equals sum(s) recomputed by torch
+        F = nfb().flows
+        from nfb200.flows.squeeze import coupling_split
+        i0, i1 = coupling_split(z, mode, bool(odd))
+        o0, o1 = coupling_split(out, mode, bool(odd))
+        assert torch.equal(i1, o1)
+        n0 = i0[0].numel()
+        pf = params.view(B, -1)
+        s = torch.tanh(pf[:, n0:]) * a + b
+        close(ldj, s.sum(1), rtol=1e-5, atol=1e-3, what='ldj')
+        close(o0.reshape(B, -1), i0.reshape(B, -1) * torch.exp(s) + pf[:, :n0], rtol=1e-5, atol=1e-5, what='z0')
+        # (3) inverse undoes forward, log-det cancels
+        back = torch.empty_like(z)
+        L.check(L.lib().nfb_affine_coupling_inv(out.data_ptr(), back.data_ptr(), params.data_ptr(), ldj.data_ptr(),
+                                                ldj.data_ptr(), a.data_ptr(), b.data_ptr(), B, C, H, W, mode, odd,
+                                                L.stream()))
+        close(back, z, rtol=1e-5, atol=1e-5, what='round trip')
+        close(ldj, torch.zeros(B), atol=1e-3, what='ldj cancels')
+
+
+def test_nll_matches_oracle():
+    n = nfb()
+    z = torch.randn(300, 3, 32, 32)
+    ldj = torch.randn(300) * 100
+    rows, total = n.gauss_nll(z.to(DEV), ldj.to(DEV))
+    ref = O.nll_rows(z, ldj)
+    close(rows, ref.float(), rtol=1e-6, atol=1e-3)
+    s, cnt = total.tolist()
+    assert cnt == 300 and abs(s - float(ref.sum())) <= 1e-6 * abs(float(ref.sum()))
+
+
+def test_errors_are_loud():
+    import nfb200._lib as L
+    n = nfb()
+    with pytest.raises(RuntimeError):
+        n.flows.Logit()(torch.rand(2, 4), torch.zeros(2))  # CPU tensor: no fallback
+    z = torch.randn(2, 3, 5, 5, device=DEV)
+    rc = L.lib().nfb_coupling_split(z.data_ptr(), z.data_ptr(), None, 2, 3, 5, 5, L.SPLIT_CHECKER, 0, L.stream())
+    assert rc == -3
+    with pytest.raises(RuntimeError):
+        L.check(rc)
