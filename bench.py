@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of the flow forward + log-det + NLL hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl nfb200|reference] [--workload NAME]
+
+One "step" = one eval-mode pass of the whole stack over one batch of synthetic inputs:
+``model.forward(x) -> (z, log_df_dz)`` followed by the Gaussian NLL reduction (and, for N > 1, the all-reduce of
+the 2-element (sum NLL, count) payload -- the only collective).  Default workload: BASELINE.json configs[1],
+Glow K=32 L=3 on 32x32x3, batch 256 per GPU (weak scaling: every rank owns its own 256 samples).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM (CUDA-graph replay,
+CUDA-event timing, max over ranks); `e2e` = the same through the public nn.Module API with pinned HOST buffers
+(H2D copy of x and D2H read of the NLL inside the timed region); `roofline` = dominant hand-written kernel, timed
+live with CUDA events; `cpu_baseline` = the CPU oracle (port of the reference's PyTorch CPU path) on the box's host
+cores.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+
+WORKLOADS = {
+    # name: (model, dims, datatype, cfg kwargs, batch per GPU, description)
+    'glow32': ('glow', (3, 32, 32), 'image', dict(layers=32, mixtures=4), 256,
+               'Glow K=32 L=3 on 32x32x3 synthetic images, batch 256 per GPU (BASELINE.json configs[1])'),
+    'flowpp32': ('flowpp', (3, 32, 32), 'image', dict(layers=32, mixtures=8), 256,
+                 'Flow++ logistic-mixture coupling on 32x32x3 synthetic, batch 256 (configs[2])'),
+    'realnvp64_rqs': ('realnvp', (64, ), None, dict(layers=8, mixtures=4, coupling='rqs'), 65536,
+                      'RealNVP 8 RQ-spline couplings on 64-dim synthetic tabular, batch 65536 (configs[3])'),
+    'realnvp64': ('realnvp', (64, ), None, dict(layers=8, mixtures=4), 65536,
+                  'RealNVP 8 affine couplings on 64-dim synthetic tabular, batch 65536 (configs[3], affine proxy)'),
+    'realnvp2': ('realnvp', (2, ), None, dict(layers=6, mixtures=4), 512,
+                 'RealNVP 6 affine couplings on 2D, batch 512 (configs[0])'),
+    'glow64': ('glow', (3, 64, 64), 'image', dict(layers=48, mixtures=4), 256,
+               'Glow K=48 L=4 on 64x64x3 synthetic, 256 per GPU = 2048 over 8 GPUs (configs[4])'),
+}
+
+
+def make_inputs(dims, datatype, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    if datatype == 'image':
+        return torch.rand((batch, ) + tuple(dims), generator=g)
+    return torch.randn((batch, ) + tuple(dims), generator=g)
+
+
+def oracle_spec(wl):
+    from oracle import flow_oracle as O
+    model, dims, datatype, cfg, _, _ = WORKLOADS[wl]
+    return O.stack_spec(model, dims, datatype, cfg['layers'], cfg.get('mixtures', 4), cfg.get('coupling'))
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'power_w_max': max(power), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def cpu_forward_timer(wl, sd, x, threads):
+    """Time the CPU oracle (port of the reference's PyTorch CPU path) on a bounded sample."""
+    from oracle import flow_oracle as O
+    spec = oracle_spec(wl)
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        z, ldj = O.stack_forward(spec, sd, x)  # warm-up
+        warm = time.perf_counter() - t0
+        best = warm
+        reps = 0
+        budget = time.perf_counter() + 20.0
+        while reps < 3 and time.perf_counter() < budget:
+            t0 = time.perf_counter()
+            z, ldj = O.stack_forward(spec, sd, x)
+            best = min(best, time.perf_counter() - t0)
+            reps += 1
+    return best, O.bits_per_dim(z, ldj), reps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference
+    cannot travel to the GPU box), all host threads, same workload/metric."""
+    if rank != 0:
+        return
+    import nfb200  # only for a state dict of the right architecture (random init, CPU tensors; no CUDA calls)
+    from oracle import flow_oracle as O
+    model, dims, datatype, cfg, batch, desc = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    net = getattr(nfb200, {'glow': 'Glow', 'flowpp': 'Flowpp', 'realnvp': 'RealNVP'}[model])(
+        dims, datatype, types.SimpleNamespace(**cfg))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec = oracle_spec(args.workload)
+    # bounded sample: size each step so the whole run stays within ~2 minutes
+    probe_n = min(batch, 16)
+    xp = make_inputs(dims, datatype, probe_n, 123)
+    with torch.no_grad():
+        O.stack_forward(spec, sd, xp)
+        t0 = time.perf_counter()
+        O.stack_forward(spec, sd, xp)
+        per_sample = (time.perf_counter() - t0) / probe_n
+    n_steps = args.steps + args.warmup
+    sample = int(max(1, min(batch, 120.0 / max(per_sample * n_steps, 1e-9))))
+    x = make_inputs(dims, datatype, sample, 0)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.stack_forward(spec, sd, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            z, ldj = O.stack_forward(spec, sd, x)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    out = {
+        'impl': 'reference', 'metric': 'samples/sec (fwd+logdet)', 'value': value, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'batch_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d samples per step of the %d-sample batch, torch %s CPU' %
+                                   (sample, batch, torch.__version__)},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+def time_kernel_stream(fn, iters, flush=None):
+    """Average device time of fn() in ms, CUDA events on the current stream, optional L2 flush between calls."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        if flush is not None:
+            flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
+
+
+def coupling_roofline(peaks):
+    """Streaming-size run of the fused affine coupling + log-det kernel (the kernel BASELINE.json's target names):
+    inputs 3 x 201 MB > L2, L2 flushed between launches, CUDA events on the launching stream."""
+    import nfb200._lib as L
+    dims, B = (3, 32, 32), 16384
+    D = 3 * 32 * 32
+    z = torch.randn((B, ) + dims, device='cuda')
+    params = torch.randn((B, ) + dims, device='cuda')
+    out = torch.empty_like(z)
+    ldj = torch.zeros(B, device='cuda')
+    a = torch.tensor([0.3], device='cuda')
+    b = torch.tensor([0.01], device='cuda')
+    flush = torch.empty(L2_BYTES * 2 // 4, device='cuda', dtype=torch.float32)
+    st = L.stream()
+
+    def run():
+        L.check(L.lib().nfb_affine_coupling_fwd(z.data_ptr(), out.data_ptr(), params.data_ptr(), ldj.data_ptr(),
+                                                ldj.data_ptr(), a.data_ptr(), b.data_ptr(), B, 3, 32, 32,
+                                                L.SPLIT_CHECKER, 0, st))
+    for _ in range(3):
+        run()
+    mean, med, best = time_kernel_stream(run, 20, flush)
+    alg = (12 * D + 8) * B  # z in 4D + (t, s) 4D + z out 4D + log-det read-modify-write
+    achieved = alg / (med * 1e-3) / 1e9
+    peak = peaks['hbm_gbs']
+    return {'kernel': 'affine_coupling_fwd (checkerboard 3x32x32, B=16384, out-of-place)', 'bound': 'hbm',
+            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'ms_per_launch': med, 'alg_bytes_per_launch': alg, 'peak_source': peaks['source'],
+            'l2': 'flushed between launches (252 MB write); inputs 604 MB > 126 MB L2'}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d.get('bf16_tflops'), 'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def run_nfb200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import nfb200
+    from nfb200 import parallel
+
+    model, dims, datatype, cfg, batch, desc = WORKLOADS[args.workload]
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    D = int(math.prod(dims))
+
+    torch.manual_seed(0)  # identical weights on every rank (replicas)
+    net = getattr(nfb200, {'glow': 'Glow', 'flowpp': 'Flowpp', 'realnvp': 'RealNVP'}[model])(
+        dims, datatype, types.SimpleNamespace(**cfg)).to(dev).eval()
+
+    # inputs: a ring of distinct batches, larger than L2 in total, pinned on the host for the e2e leg
+    bytes_per_batch = batch * D * 4
+    ring_n = max(4, min(64, L2_BYTES * 5 // 4 // bytes_per_batch + 1))
+    host_ring = [make_inputs(dims, datatype, batch, 1000 * rank + i).pin_memory() for i in range(ring_n)]
+    dev_ring = [h.to(dev) for h in host_ring]
+
+    with torch.no_grad():
+        net(dev_ring[0])  # ActNorm data-dependent init (modules.py:238-244) + weight caches
+        torch.cuda.synchronize()
+
+        # ---- launches per step (eager) -----------------------------------------------------------
+        n0 = nfb200._lib.launch_count()
+        z, ldj = net(dev_ring[0])
+        rows, total = nfb200.gauss_nll(z, ldj)
+        launches_per_step = nfb200._lib.launch_count() - n0
+        torch.cuda.synchronize()
+
+        # ---- CUDA graph of one step ---------------------------------------------------------------
+        x_static = dev_ring[0].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                z, ldj = net(x_static)
+                rows, total = nfb200.gauss_nll(z, ldj)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            z, ldj = net(x_static)
+            rows, total = nfb200.gauss_nll(z, ldj)
+        tot_red = torch.zeros(2, device=dev, dtype=torch.float64)
+
+        def step(i):
+            x_static.copy_(dev_ring[i % ring_n], non_blocking=True)
+            graph.replay()
+            if world > 1:
+                tot_red.copy_(total)
+                dist.all_reduce(tot_red)
+
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        t_wall = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t_wall
+        ms = e0.elapsed_time(e1)
+        if ms * 1e-3 < 1.0 and rank == 0:
+            # make sure the clock sampler saw the load: keep the GPU busy a little longer (untimed)
+            t_end = time.perf_counter() + 1.0
+            while time.perf_counter() < t_end:
+                step(0)
+            torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        value = batch * world * args.steps / (ms * 1e-3)
+
+        # ---- end-to-end leg: public API, pinned host inputs, result read back every step ------------------
+        host_total = torch.zeros(2, dtype=torch.float64).pin_memory()
+        host_rows = torch.zeros(batch, dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            x_static.copy_(host_ring[i % ring_n], non_blocking=True)  # H2D from pinned memory
+            graph.replay()  # net.forward + gauss_nll as captured from the public API
+            if world > 1:
+                tot_red.copy_(total)
+                dist.all_reduce(tot_red)
+                host_total.copy_(tot_red, non_blocking=True)
+            else:
+                host_total.copy_(total, non_blocking=True)
+            host_rows.copy_(rows, non_blocking=True)  # per-sample NLL (= -log p(y), main.py:121-124)
+            torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+            return host_total[0].item()
+
+        for i in range(args.warmup):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            e2e_step(args.warmup + i)
+        s1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e_value = batch * world * args.steps / (e2e_ms * 1e-3)
+
+        # ---- bits/dim of the (global) batch ring[0] ------------------------------------------------------
+        x_static.copy_(dev_ring[0])
+        graph.replay()
+        bpd_local = nfb200.bits_per_dim_from_total(total, D)
+        bpd_global = parallel.global_bits_per_dim(total, D)
+        torch.cuda.synchronize()
+
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    roof = None
+    try:
+        roof = coupling_roofline(peaks)
+    except Exception as e:  # the roofline probe must never take the bench line down
+        roof = {'error': repr(e)}
+
+    # ---- CPU baseline on the box's host cores: oracle port, bounded sample ---------------------------------
+    threads = os.cpu_count() or 1
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    cpu_n = batch if model != 'flowpp' else min(batch, 32)
+    if args.workload == 'glow64':
+        cpu_n = 32
+    xs = host_ring[0][:cpu_n].clone()
+    best, bpd_cpu, reps = cpu_forward_timer(args.workload, sd, xs, threads)
+    # GPU bits/dim on exactly the CPU's sample
+    with torch.no_grad():
+        bpd_gpu_sample = net.bits_per_dim(xs.to(dev))
+    cpu = {'value': cpu_n / best, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+           'sample': 'best of %d forwards over %d samples of ring[0] (%.2f s each), torch %s CPU, oracle/flow_oracle.py'
+                     % (max(reps, 1), cpu_n, best, torch.__version__)}
+
+    out = {
+        'metric': 'samples/sec (fwd+logdet)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'batch_per_gpu': batch, 'global_batch': batch * world,
+                   'l2': 'inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)' %
+                         (ring_n, ring_n * bytes_per_batch / 1e6),
+                   'parallelism': 'sample-sharded replicas x%d, all-reduce of (sum NLL, count) only' % world,
+                   'timing': 'CUDA events around K graph replays, max over ranks', 'wall_s': wall},
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
+                'h2d_bytes_per_step': bytes_per_batch, 'd2h_bytes_per_step': 16 + 4 * batch},
+        'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
+        'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        'bits_per_dim': {'gpu_global_batch': bpd_global, 'gpu_rank0_batch': bpd_local, 'gpu_on_cpu_sample': bpd_gpu_sample,
+                         'cpu_oracle_on_sample': bpd_cpu,
+                         'rel_err': abs(bpd_gpu_sample - bpd_cpu) / abs(bpd_cpu), 'tolerance': 1e-5},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='nfb200', choices=['nfb200', 'reference'])
+    ap.add_argument('--workload', default='glow32', choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'nfb200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_nfb200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

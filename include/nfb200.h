@@ -164,6 +164,26 @@ int nfb_gauss_nll(const float* z, const float* ldj, float* nll_rows, double* sum
  * v (O, I*kk), g (I*kk) -> w_out (O, I*kk). */
 int nfb_weight_norm(const float* v, const float* g, float* w_out, int O, int Ikk, float eps, nfb_stream_t stream);
 
+/* ConvNet (modules.py:416-438) / MLP (modules.py:391-413) in eval mode as ONE kernel.
+ * nfb_resnet_pack folds WeightNorm, and every BatchNorm that directly follows a conv/linear, into one packed weight
+ * buffer (nfb_resnet_pack_size floats; call again whenever a parameter changes).  `tensors` is a HOST array of 38
+ * device pointers: (weight_v, weight_g, bias) of in_block.0, mid_block.0.net.2, mid_block.0.net.5, mid_block.1.net.2,
+ * mid_block.1.net.5, out_block.2, then (weight, bias, running_mean, running_var) of mid_block.0.net.0,
+ * mid_block.0.net.3, mid_block.1.net.0, mid_block.1.net.3, out_block.0.  conv != 0: ConvNet (3x3 / 1x1), else MLP. */
+int nfb_resnet_pack_size(int in_ch, int out_ch, int conv);
+int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int out_ch, int conv, float wn_eps,
+                    float bn_eps, nfb_stream_t stream);
+/* params_out (B, out_ch, h, w) = ConvNet(z1).  mode = NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL: `src` is the coupling's
+ * z (B, C, H, W) and the conditioner input z1 = the pass-through half is gathered on the fly (coupling.py:33,105);
+ * mode < 0: `src` is the (B, in_ch, H, W) conditioner input itself (C ignored).  Supported spatial sizes of the
+ * conditioner input: 16x16, 8x8, 4x4 (else NFB_ERR_UNSUPPORTED). */
+int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
+                    int odd, int in_ch, int out_ch, nfb_stream_t stream);
+/* params_out (B, out_ch) = MLP(z1).  mode = NFB_SPLIT_1D: src = z (B, C), z1 gathered (squeeze.py:64-72);
+ * mode < 0: src = (B, in_ch). */
+int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd, int in_ch,
+                int out_ch, nfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libnfb200.so')
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'nfb200.h')
 
 SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
+ERR_NULL, ERR_SHAPE, ERR_SPLIT, ERR_UNSUPPORTED = -1, -2, -3, -4
 
 _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 
@@ -45,6 +46,10 @@ _SIGNATURES = {
     'nfb_unsqueeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nfb_gauss_nll': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_weight_norm': [_P, _P, _P, _I, _I, _F, _P],
+    'nfb_resnet_pack_size': [_I, _I, _I],
+    'nfb_resnet_pack': [_P, _P, _I, _I, _I, _F, _F, _P],
+    'nfb_convnet_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong}
 

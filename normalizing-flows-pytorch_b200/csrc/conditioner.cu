@@ -1,0 +1,511 @@
+// conditioner.cu -- the couplings' conditioner networks (modules.py:342-438, weight_norm.py) as ONE kernel per call.
+//
+// ConvNet: conv3x3(in->32) -> 2 x [BN, ReLU, conv3x3, BN, ReLU, conv3x3] + skip -> BN, ReLU, conv1x1(32->out);
+// MLP: the same with Linear layers.  Eval mode: WeightNorm and the BatchNorm that directly follows a conv are folded
+// into packed weights once per weight update (nfb_pack_*), the remaining BatchNorms are per-channel scale/shift.
+//
+// Design (B200): the 32-channel activations of a whole sample never leave the SM -- the residual stream lives in
+// registers (each thread owns 8 output channels x 4 consecutive pixels for every layer), the ReLU'd conv input lives
+// in shared memory with zero rows above/below (x borders by predication, x neighbours by warp shuffle), and the
+// 36.9 KB of weights per 3x3 layer are streamed L2 -> shared memory with cp.async, double-buffered so the next
+// layer's weights land while the current layer computes.  The conditioner input z1 is gathered straight from z with
+// the coupling's split addressing (no materialised split).  Arithmetic is FP32 FFMA: bits/dim parity at 1e-5 with a
+// reference noise floor of 2e-7 rules out single-pass TF32/BF16 tensor-core math; an error-compensated
+// tcgen05 path is the next step.
+#include "common.cuh"
+
+namespace nfb {
+
+constexpr int kF = 32;            // base_filters of every conditioner in the reference (modules.py:392,417)
+constexpr int kWStage = 9 * kF * kF;  // floats of one 32->32 3x3 layer
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// packing (once per weight update)
+// ---------------------------------------------------------------------------------------------------------
+// One weight-normalised layer: v (O, I, kk), g (I, kk), bias (O)  ->  w_out laid out [(i*kk+tap)][chunk][32] with
+// o = chunk*32 + lane, i.e. index ((o/32) * I*kk + i*kk + tap) * 32 + o%32  (rows of 32 output channels; for O <= 32
+// a single chunk).  Optionally folds a BatchNorm (eval) that directly follows the layer:
+//   y = ((conv + b) - rm) / sqrt(rv + eps) * gamma + beta.
+__global__ void __launch_bounds__(128) pack_wn_kernel(const float* __restrict__ v, const float* __restrict__ gw,
+                                                     const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                     const float* __restrict__ bn_b, const float* __restrict__ bn_rm,
+                                                     const float* __restrict__ bn_rv, float* __restrict__ w_out,
+                                                     float* __restrict__ b_out, int O, int J /* I*kk */, int O_pad,
+                                                     float wn_eps, float bn_eps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < J) {
+        float ss = 0.f;
+        for (int o = 0; o < O; ++o) { const float x = v[static_cast<size_t>(o) * J + j]; ss = fmaf(x, x, ss); }
+        const float scale = __fdiv_rn(gw[j], __fadd_rn(sqrtf(ss), wn_eps));  // weight_norm.py:40
+        for (int o = 0; o < O_pad; ++o) {
+            float w = 0.f;
+            if (o < O) {
+                w = __fmul_rn(v[static_cast<size_t>(o) * J + j], scale);
+                if (bn_w) w *= bn_w[o] / sqrtf(bn_rv[o] + bn_eps);
+            }
+            w_out[(static_cast<size_t>(o >> 5) * J + j) * 32 + (o & 31)] = w;
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int o = threadIdx.x; o < O_pad; o += blockDim.x) {
+            float b = 0.f;
+            if (o < O) {
+                b = bias[o];
+                if (bn_w) {
+                    const float sc = bn_w[o] / sqrtf(bn_rv[o] + bn_eps);
+                    b = (b - bn_rm[o]) * sc + bn_b[o];
+                }
+            }
+            b_out[o] = b;
+        }
+    }
+}
+
+// BatchNorm (eval) as scale/shift: y = x*scale + shift
+__global__ void pack_bn_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float* __restrict__ scale, float* __restrict__ shift, int C,
+                               float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        const float sc = w[c] / sqrtf(rv[c] + eps);
+        scale[c] = sc;
+        shift[c] = b[c] - rm[c] * sc;
+    }
+}
+
+// packed buffer offsets (in floats); every section is a multiple of 32 floats (128 B)
+struct PackLayout {
+    int w0, b0;
+    int bnA[2], w1[2], b1[2], w2[2], b2[2];
+    int bnO, wout, bout;
+    int total;
+};
+__host__ __device__ inline PackLayout pack_layout(int Cin, int Cout, int kk) {
+    PackLayout L;
+    const int CoutPad = (Cout + 31) & ~31;
+    int o = 0;
+    L.w0 = o; o += Cin * kk * kF;
+    L.b0 = o; o += kF;
+    for (int i = 0; i < 2; ++i) {
+        L.bnA[i] = o; o += 2 * kF;
+        L.w1[i] = o; o += kF * kk * kF;
+        L.b1[i] = o; o += kF;
+        L.w2[i] = o; o += kF * kk * kF;
+        L.b2[i] = o; o += kF;
+    }
+    L.bnO = o; o += 2 * kF;
+    L.wout = o; o += kF * CoutPad;
+    L.bout = o; o += CoutPad;
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused ConvNet
+// ---------------------------------------------------------------------------------------------------------
+// 8 output channels x 4 pixels per thread, one 3x3 layer over CI input channels held in shared memory.
+template <int H, int W>
+__device__ __forceinline__ void conv3x3_acc(float (&acc)[8][4], const float* __restrict__ a_base /* bufA + sample base */,
+                                            int chs, const float* __restrict__ wst /* [ci][9][32] */, int CI, int og,
+                                            int y, int x0) {
+    const bool left_edge = (x0 == 0), right_edge = (x0 + 4 == W);
+    for (int ci = 0; ci < CI; ++ci) {
+        const float* a = a_base + ci * chs + y * W + x0;  // padded row index y+ky, ky = 0..2
+        const float* wrow = wst + ci * 9 * kF + og * 8;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const float4 c = ld4(a + ky * W);
+            float l = 0.f, r = 0.f;
+            if (W > 4) {
+                l = __shfl_up_sync(0xffffffffu, c.w, 1);
+                r = __shfl_down_sync(0xffffffffu, c.x, 1);
+                if (left_edge) l = 0.f;
+                if (right_edge) r = 0.f;
+            }
+            const float av[6] = {l, c.x, c.y, c.z, c.w, r};
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 w0 = ld4(wrow + (ky * 3 + kx) * kF);
+                const float4 w1 = ld4(wrow + (ky * 3 + kx) * kF + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int o = 0; o < 8; ++o)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[o][p] = fmaf(wv[o], av[p + kx], acc[o][p]);
+            }
+        }
+    }
+}
+
+// MODE: NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL gather z1 from the coupling's z; MODE < 0: x is the (B,Cin,H,W) input.
+template <int H, int W, int NT, int MODE>
+__global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
+                                                          const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
+                                                          int B) {
+    constexpr int PGS = H * W / 4;         // pixel groups per sample
+    constexpr int NPG = NT / 4;            // pixel groups per CTA
+    constexpr int S = NPG / PGS;           // samples per CTA
+    static_assert(S >= 1 && S * PGS == NPG, "tile must hold whole samples");
+    constexpr int CHS = S * (H + 2) * W;   // channel stride of bufA (rows 0 and H+1 of every sample stay zero)
+    extern __shared__ __align__(16) float smem[];
+    float* bufA = smem;                    // [32][S][H+2][W]
+    float* wbuf = smem + kF * CHS;         // [2][kWStage]
+
+    const PackLayout L = pack_layout(Cin, Cout, 9);
+    const int CoutPad = (Cout + 31) & ~31;
+    const int t = threadIdx.x;
+    const int pg = t % NPG, og = t / NPG;
+    const int s = pg / PGS, r = pg % PGS;
+    const int y = r / (W / 4), x0 = 4 * (r % (W / 4));
+    const int b = blockIdx.x * S + s;
+    const bool valid = b < B;
+    const int sbase = s * (H + 2) * W;
+
+    int pf_cnt = 0, use_cnt = 0;
+    auto prefetch = [&](const float* src, int nfloats) {
+        float* dst = wbuf + (pf_cnt & 1) * kWStage;
+        for (int i = t * 4; i < nfloats; i += NT * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+        ++pf_cnt;
+    };
+    auto acquire = [&]() -> const float* {
+        cp_async_wait_all();
+        __syncthreads();
+        const float* w = wbuf + (use_cnt & 1) * kWStage;
+        ++use_cnt;
+        return w;
+    };
+
+    // weight stage schedule: in-conv chunks, 4 mid layers, out chunks
+    const int n_in = (Cin + kF - 1) / kF;
+    const int n_out = CoutPad / kF;
+    const int n_stage = n_in + 4 + n_out;
+    auto stage_src = [&](int i, int& n) -> const float* {
+        if (i < n_in) {
+            const int ci = (Cin - i * kF) < kF ? (Cin - i * kF) : kF;
+            n = ci * 9 * kF;
+            return pk + L.w0 + i * kF * 9 * kF;
+        }
+        i -= n_in;
+        if (i < 4) { n = kWStage; return pk + ((i & 1) ? L.w2[i >> 1] : L.w1[i >> 1]); }
+        i -= 4;
+        n = kF * kF;
+        return pk + L.wout + i * kF * kF;
+    };
+    int stage = 0;
+    auto prefetch_stage = [&](int i) {
+        if (i < n_stage) { int n; const float* src = stage_src(i, n); prefetch(src, n); }
+    };
+
+    prefetch_stage(0);
+    for (int i = t; i < kF * CHS; i += NT) bufA[i] = 0.f;  // includes the zero halo rows
+    __syncthreads();
+
+    float xres[8][4];  // residual stream: this thread's 8 channels x 4 pixels
+    float acc[8][4];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+
+    // ---- in conv: Cin -> 32, input channels in chunks of 32 ---------------------------------------------
+    for (int c = 0; c < n_in; ++c) {
+        const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
+        if (c > 0) __syncthreads();  // everyone finished reading the previous chunk
+        for (int i = t; i < CI * S * H * W; i += NT) {
+            const int ci = i / (S * H * W);
+            int rem = i - ci * (S * H * W);
+            const int ss = rem / (H * W);
+            rem -= ss * (H * W);
+            const int bb = blockIdx.x * S + ss;
+            float v = 0.f;
+            if (bb < B) {
+                const int j = (c * kF + ci) * (H * W) + rem;  // index inside the (Cin, H, W) conditioner input
+                if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(bb) * Cin * (H * W) + j);
+                else v = __ldg(zsrc + static_cast<size_t>(bb) * g.D + half_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, j, 1));
+            }
+            bufA[ci * CHS + ss * (H + 2) * W + W + rem] = v;  // +W: skip the zero row above
+        }
+        const float* w = acquire();
+        prefetch_stage(++stage);
+        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, CI, og, y, x0);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const float bias = __ldg(pk + L.b0 + og * 8 + o);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) xres[o][p] = acc[o][p] + bias;
+    }
+
+    // write relu(scale*v + shift) of this thread's tile into bufA (after everyone finished reading it)
+    auto store_act = [&](const float (&v)[8][4], const float* sc_sh) {
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int ch = og * 8 + o;
+            const float sc = sc_sh ? __ldg(sc_sh + ch) : 1.f, sh = sc_sh ? __ldg(sc_sh + kF + ch) : 0.f;
+            float4 q;
+            q.x = fmaxf(fmaf(v[o][0], sc, sh), 0.f);
+            q.y = fmaxf(fmaf(v[o][1], sc, sh), 0.f);
+            q.z = fmaxf(fmaf(v[o][2], sc, sh), 0.f);
+            q.w = fmaxf(fmaf(v[o][3], sc, sh), 0.f);
+            st4(bufA + ch * CHS + sbase + (y + 1) * W + x0, q);
+        }
+    };
+
+    // ---- two residual blocks ------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+        store_act(xres, pk + L.bnA[blk]);
+        const float* w = acquire();
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const float bias = __ldg(pk + L.b1[blk] + og * 8 + o);  // second BN folded into (w1, b1)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] += bias;
+        }
+        store_act(acc, nullptr);  // relu only
+        w = acquire();
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const float bias = __ldg(pk + L.b2[blk] + og * 8 + o);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) xres[o][p] += acc[o][p] + bias;
+        }
+    }
+
+    // ---- out block: BN, ReLU, conv1x1 32 -> Cout in chunks of 32 output channels ---------------------------------
+    store_act(xres, pk + L.bnO);
+    for (int c = 0; c < n_out; ++c) {
+        const float* w = acquire();  // [32 ic][32 oc]
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        const float* a = bufA + sbase + (y + 1) * W + x0;
+#pragma unroll 4
+        for (int ci = 0; ci < kF; ++ci) {
+            const float4 v = ld4(a + ci * CHS);
+            const float4 w0 = ld4(w + ci * kF + og * 8), w1 = ld4(w + ci * kF + og * 8 + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                acc[o][0] = fmaf(wv[o], v.x, acc[o][0]);
+                acc[o][1] = fmaf(wv[o], v.y, acc[o][1]);
+                acc[o][2] = fmaf(wv[o], v.z, acc[o][2]);
+                acc[o][3] = fmaf(wv[o], v.w, acc[o][3]);
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int oc = c * kF + og * 8 + o;
+                if (oc < Cout) {
+                    const float bias = __ldg(pk + L.bout + oc);
+                    st4(out + ((static_cast<size_t>(b) * Cout + oc) * H + y) * W + x0,
+                        make_float4(acc[o][0] + bias, acc[o][1] + bias, acc[o][2] + bias, acc[o][3] + bias));
+                }
+            }
+        }
+    }
+}
+
+template <int H, int W, int NT, int MODE>
+static int launch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
+                          cudaStream_t st) {
+    constexpr int S = (NT / 4) / (H * W / 4);
+    constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 2 * kWStage) * sizeof(float);
+    auto kern = convnet_fused_kernel<H, W, NT, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = true;
+    }
+    kern<<<(B + S - 1) / S, NT, smem, st>>>(zsrc, out, pk, g, Cin, Cout, B);
+    return launch_status();
+}
+
+template <int MODE>
+static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
+                            int h, int w, cudaStream_t st) {
+    if (h == 16 && w == 16) return launch_convnet<16, 16, 256, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
+    if (h == 8 && w == 8) return launch_convnet<8, 8, 64, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
+    if (h == 4 && w == 4) return launch_convnet<4, 4, 32, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
+    return NFB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused MLP (1-D couplings): one thread per sample, the 32 hidden activations in registers, weights in shared memory
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>  // NFB_SPLIT_1D gathers z1 from z (row stride g.D); MODE < 0: x is (B, Cin)
+__global__ void __launch_bounds__(128) mlp_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
+                                                       const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
+                                                       int B) {
+    extern __shared__ __align__(16) float sw[];  // the whole packed network
+    const PackLayout L = pack_layout(Cin, Cout, 1);
+    for (int i = threadIdx.x * 4; i < L.total; i += blockDim.x * 4) st4(sw + i, ldg4(pk + i));
+    __syncthreads();
+    const int CoutPad = (Cout + 31) & ~31;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x[kF], a[kF], y[kF];
+#pragma unroll
+        for (int o = 0; o < kF; ++o) x[o] = sw[L.b0 + o];
+        for (int ci = 0; ci < Cin; ++ci) {
+            float v;
+            if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(b) * Cin + ci);
+            else v = __ldg(zsrc + static_cast<size_t>(b) * g.D + 2 * ci + (g.odd ? 0 : 1));  // z1 of squeeze1d
+            const float* wr = sw + L.w0 + ci * kF;
+#pragma unroll
+            for (int o = 0; o < kF; ++o) x[o] = fmaf(wr[o], v, x[o]);
+        }
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+            for (int o = 0; o < kF; ++o)
+                a[o] = fmaxf(fmaf(x[o], sw[L.bnA[blk] + o], sw[L.bnA[blk] + kF + o]), 0.f);
+#pragma unroll
+            for (int o = 0; o < kF; ++o) y[o] = sw[L.b1[blk] + o];
+#pragma unroll
+            for (int ci = 0; ci < kF; ++ci) {
+                const float* wr = sw + L.w1[blk] + ci * kF;
+#pragma unroll
+                for (int o = 0; o < kF; ++o) y[o] = fmaf(wr[o], a[ci], y[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < kF; ++o) { a[o] = fmaxf(y[o], 0.f); y[o] = sw[L.b2[blk] + o]; }
+#pragma unroll
+            for (int ci = 0; ci < kF; ++ci) {
+                const float* wr = sw + L.w2[blk] + ci * kF;
+#pragma unroll
+                for (int o = 0; o < kF; ++o) y[o] = fmaf(wr[o], a[ci], y[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < kF; ++o) x[o] += y[o];
+        }
+#pragma unroll
+        for (int o = 0; o < kF; ++o) a[o] = fmaxf(fmaf(x[o], sw[L.bnO + o], sw[L.bnO + kF + o]), 0.f);
+        for (int c = 0; c < CoutPad / kF; ++c) {
+#pragma unroll
+            for (int o = 0; o < kF; ++o) y[o] = sw[L.bout + c * kF + o];
+#pragma unroll
+            for (int ci = 0; ci < kF; ++ci) {
+                const float* wr = sw + L.wout + (c * kF + ci) * kF;
+#pragma unroll
+                for (int o = 0; o < kF; ++o) y[o] = fmaf(wr[o], a[ci], y[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < kF; ++o)
+                if (c * kF + o < Cout) out[static_cast<size_t>(b) * Cout + c * kF + o] = y[o];
+        }
+    }
+}
+
+}  // namespace nfb
+
+using namespace nfb;
+
+extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
+    if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
+    return pack_layout(in_ch, out_ch, conv ? 9 : 1).total;
+}
+
+extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, int out_ch, int conv, float wn_eps,
+                               float bn_eps, nfb_stream_t stream) {
+    // t[0..17]: (v, g, bias) of in_block.0, mid0.net.2, mid0.net.5, mid1.net.2, mid1.net.5, out_block.2
+    // t[18..37]: (weight, bias, running_mean, running_var) of mid0.net.0, mid0.net.3, mid1.net.0, mid1.net.3, out_block.0
+    if (!t || !packed) return NFB_ERR_NULL;
+    for (int i = 0; i < 38; ++i)
+        if (!t[i]) return NFB_ERR_NULL;
+    if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
+    const int kk = conv ? 9 : 1;
+    const PackLayout L = pack_layout(in_ch, out_ch, kk);
+    const int CoutPad = (out_ch + 31) & ~31;
+    cudaStream_t st = as_stream(stream);
+    auto wn = [&](int li, int bn /* -1: none */, float* w, float* b, int O, int J, int Opad) {
+        const float* const* q = t + 3 * li;
+        const float* const* n = bn >= 0 ? t + 18 + 4 * bn : nullptr;
+        pack_wn_kernel<<<(J + 127) / 128, 128, 0, st>>>(q[0], q[1], q[2], n ? n[0] : nullptr, n ? n[1] : nullptr,
+                                                        n ? n[2] : nullptr, n ? n[3] : nullptr, w, b, O, J, Opad, wn_eps,
+                                                        bn_eps);
+        return launch_status();
+    };
+    auto bn = [&](int bi, float* dst) {
+        const float* const* n = t + 18 + 4 * bi;
+        pack_bn_kernel<<<1, kF, 0, st>>>(n[0], n[1], n[2], n[3], dst, dst + kF, kF, bn_eps);
+        return launch_status();
+    };
+    int rc;
+    if ((rc = wn(0, -1, packed + L.w0, packed + L.b0, kF, in_ch * kk, kF))) return rc;
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = bn(2 * i, packed + L.bnA[i]))) return rc;
+        if ((rc = wn(1 + 2 * i, 2 * i + 1, packed + L.w1[i], packed + L.b1[i], kF, kF * kk, kF))) return rc;
+        if ((rc = wn(2 + 2 * i, -1, packed + L.w2[i], packed + L.b2[i], kF, kF * kk, kF))) return rc;
+    }
+    if ((rc = bn(4, packed + L.bnO))) return rc;
+    return wn(5, -1, packed + L.wout, packed + L.bout, out_ch, kF, CoutPad);
+}
+
+extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
+                               int mode, int odd, int in_ch, int out_ch, nfb_stream_t stream) {
+    if (!src || !params_out || !packed) return NFB_ERR_NULL;
+    if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
+    cudaStream_t st = as_stream(stream);
+    SplitGeom g;
+    if (mode < 0) {  // src is the (B, in_ch, H, W) conditioner input itself
+        if (B <= 0 || H <= 0 || W <= 0) return NFB_ERR_SHAPE;
+        g = SplitGeom{};
+        return dispatch_convnet<-1>(src, params_out, packed, g, in_ch, out_ch, B, H, W, st);
+    }
+    const int rc = make_geom(g, B, C, H, W, mode, odd);
+    if (rc != NFB_OK) return rc;
+    if (g.c0 != in_ch) return NFB_ERR_SHAPE;
+    if (mode == NFB_SPLIT_CHECKER) return dispatch_convnet<NFB_SPLIT_CHECKER>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
+    if (mode == NFB_SPLIT_CHANNEL) return dispatch_convnet<NFB_SPLIT_CHANNEL>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
+    return NFB_ERR_SHAPE;
+}
+
+extern "C" int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd,
+                           int in_ch, int out_ch, nfb_stream_t stream) {
+    if (!src || !params_out || !packed) return NFB_ERR_NULL;
+    if (in_ch <= 0 || out_ch <= 0 || B <= 0) return NFB_ERR_SHAPE;
+    const PackLayout L = pack_layout(in_ch, out_ch, 1);
+    const size_t smem = static_cast<size_t>(L.total) * sizeof(float);
+    if (smem > 200 * 1024) return NFB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    SplitGeom g{};
+    int blocks = (B + 127) / 128;
+    if (blocks > kSMs * 4) blocks = kSMs * 4;
+    if (mode < 0) {
+        auto kern = mlp_fused_kernel<-1>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<blocks, 128, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
+        return launch_status();
+    }
+    const int rc = make_geom(g, B, C, 1, 1, NFB_SPLIT_1D, odd);
+    if (rc != NFB_OK) return rc;
+    if (mode != NFB_SPLIT_1D || g.c0 != in_ch) return NFB_ERR_SHAPE;
+    auto kern = mlp_fused_kernel<NFB_SPLIT_1D>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<blocks, 128, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
+    return launch_status();
+}

@@ -3,6 +3,8 @@
 ``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
 -> out_block (BN, ReLU, WN-layer).  Eval mode only (running statistics).
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -46,7 +48,80 @@ class _ResNetConditioner(nn.Module):
         self.mid_block = nn.Sequential(*[_ResBlock(base_filters, self.conv) for _ in range(n_blocks)])
         self.out_block = nn.Sequential(bn(base_filters), nn.ReLU(inplace=True), WeightNorm(last))
 
-    # -- building blocks of the eval-mode forward -------------------------------------------------------
+    # -- packed (WeightNorm + BatchNorm folded) weights for the fused kernel, rebuilt when any tensor changes ----
+    def _tensors(self):
+        wn = [self.in_block[0]] + [blk.net[i] for blk in self.mid_block for i in (2, 5)] + [self.out_block[2]]
+        bn = [blk.net[i] for blk in self.mid_block for i in (0, 3)] + [self.out_block[0]]
+        ts = []
+        for m in wn:
+            ts += [m.module.weight_v, m.module.weight_g, m.module.bias]
+        for m in bn:
+            ts += [m.weight, m.bias, m.running_mean, m.running_var]
+        return ts, wn[0].eps, bn[0].eps
+
+    def packed(self):
+        ts, wn_eps, bn_eps = self._tensors()
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if key != getattr(self, '_pack_key', None):
+            if len(self.mid_block) != 2 or self.base_filters != 32:
+                raise NotImplementedError('fused conditioner kernel is built for base_filters=32, n_blocks=2 '
+                                          '(every use in the reference)')
+            dev = ts[0].device
+            n = L.lib().nfb_resnet_pack_size(self.in_channels, self.out_channels, int(self.conv))
+            if n <= 0:
+                L.check(n)
+            self._pack = torch.empty(n, device=dev, dtype=torch.float32)
+            arr = (ctypes.c_void_p * 38)(*[L.ptr(L.dev(t.data, 'conditioner parameter')) for t in ts])
+            L.check(L.lib().nfb_resnet_pack(arr, L.ptr(self._pack), self.in_channels, self.out_channels,
+                                            int(self.conv), float(wn_eps), float(bn_eps), L.stream()))
+            self._pack_key = key
+        return self._pack
+
+    def _check_mode(self):
+        if self.training:
+            raise RuntimeError('nfb200 conditioners implement the eval-mode (running statistics) path only')
+
+    def forward(self, x):
+        """params = net(x) for an explicit conditioner input x: (B, in, h, w) or (B, in)."""
+        self._check_mode()
+        x = L.dev(x, 'conditioner input')
+        B = x.size(0)
+        if self.conv:
+            h, w = x.size(2), x.size(3)
+            out = torch.empty((B, self.out_channels, h, w), device=x.device, dtype=torch.float32)
+            rc = L.lib().nfb_convnet_fwd(L.ptr(x), L.ptr(out), L.ptr(self.packed()), B, 0, h, w, -1, 0,
+                                         self.in_channels, self.out_channels, L.stream())
+            if rc == L.ERR_UNSUPPORTED:
+                return self._forward_library(x)
+        else:
+            out = torch.empty((B, self.out_channels), device=x.device, dtype=torch.float32)
+            rc = L.lib().nfb_mlp_fwd(L.ptr(x), L.ptr(out), L.ptr(self.packed()), B, 0, -1, 0, self.in_channels,
+                                     self.out_channels, L.stream())
+        L.check(rc)
+        return out
+
+    def forward_from_z(self, z, mode, odd):
+        """params = net(z1) with z1 (the pass-through half of the coupling split) gathered inside the kernel."""
+        self._check_mode()
+        B = z.size(0)
+        if self.conv:
+            _, C, H, W = z.shape
+            h, w = (H // 2, W // 2) if mode == L.SPLIT_CHECKER else (H, W)
+            out = torch.empty((B, self.out_channels, h, w), device=z.device, dtype=torch.float32)
+            rc = L.lib().nfb_convnet_fwd(L.ptr(z), L.ptr(out), L.ptr(self.packed()), B, C, H, W, mode, int(odd),
+                                         self.in_channels, self.out_channels, L.stream())
+            if rc == L.ERR_UNSUPPORTED:
+                return None
+        else:
+            out = torch.empty((B, self.out_channels), device=z.device, dtype=torch.float32)
+            rc = L.lib().nfb_mlp_fwd(L.ptr(z), L.ptr(out), L.ptr(self.packed()), B, z.size(1), mode, int(odd),
+                                     self.in_channels, self.out_channels, L.stream())
+        L.check(rc)
+        return out
+
+    # -- library path (cuDNN / cuBLAS through torch, TF32 off): only for conditioner inputs whose spatial size the
+    #    fused kernel does not cover yet (anything but 16x16 / 8x8 / 4x4, e.g. the 32x32 level of a 64x64 Glow), and
+    #    as an on-device cross-check in the tests -------------------------------------------------------------
     def _layer(self, wn, x):
         w = wn.weight()
         if self.conv:
@@ -57,9 +132,8 @@ class _ResNetConditioner(nn.Module):
     def _bn_relu(bn, x):
         return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
 
-    def forward(self, x):
-        if self.training:
-            raise RuntimeError('nfb200 conditioners implement the eval-mode (running statistics) path only')
+    def _forward_library(self, x):
+        self._check_mode()
         x = L.dev(x, 'conditioner input')
         with torch.no_grad():
             x = self._layer(self.in_block[0], x)

@@ -43,8 +43,13 @@ class AbstractCoupling(nn.Module):
         return tuple(z.shape)
 
     def _params(self, z):
+        net = self.net
+        if hasattr(net, 'forward_from_z'):  # fused conditioner: gathers z1 from z inside the kernel
+            p = net.forward_from_z(z, self.mode, self.odd)
+            if p is not None:
+                return p
         _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
-        return L.dev(self.net(z1), 'conditioner output')
+        return L.dev(net(z1), 'conditioner output')
 
     def forward(self, z, log_df_dz):
         return self._run(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), False)
@@ -64,6 +69,9 @@ class AdditiveCoupling(AbstractCoupling):
         self.net_t = MLP(in_chs, out_chs) if len(dims) == 1 else ConvNet(in_chs, out_chs)
 
     def _params(self, z):
+        p = self.net_t.forward_from_z(z, self.mode, self.odd)
+        if p is not None:
+            return p
         _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
         return L.dev(self.net_t(z1), 'conditioner output')
 
