@@ -142,6 +142,13 @@ int nfb_invconv1x1_weight(const float* P, const float* L, const float* U, const 
 int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
                          const float* log_s, float sign, int B, int C, int HW, nfb_stream_t stream);
 
+/* Fused flow-step front end: ActNorm.forward (modules.py:246-250) followed by InvertibleConv1x1.forward
+ * (modules.py:470-482) in one pass over z -- bit-identical to the two calls back to back.  Returns
+ * NFB_ERR_UNSUPPORTED for shapes the tiled kernel does not take (HW % 4 != 0): run the layers separately. */
+int nfb_actnorm_invconv_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out,
+                            const float* log_scale, const float* bias, const float* W, const float* log_s, int B, int C,
+                            int HW, nfb_stream_t stream);
+
 /* ---------------- Squeeze2d / Unsqueeze2d (squeeze.py:153-189) ---------------- */
 
 /* (B,C,H,W) -> (B,4C,H/2,W/2): out[b,4c+2dy+dx,i,j] = in[b,c,2i+dy,2j+dx]; odd swaps the two channel halves. */
@@ -171,6 +178,8 @@ int nfb_weight_norm(const float* v, const float* g, float* w_out, int O, int Ikk
  * mid_block.1.net.5, out_block.2, then (weight, bias, running_mean, running_var) of mid_block.0.net.0,
  * mid_block.0.net.3, mid_block.1.net.0, mid_block.1.net.3, out_block.0.  conv != 0: ConvNet (3x3 / 1x1), else MLP. */
 int nfb_resnet_pack_size(int in_ch, int out_ch, int conv);
+/* developer knob: select a kernel variant (key 0/1/2: ConvNet at 16x16 / 8x8 / 4x4; value 0 = default). */
+int nfb_set_tuning(int key, int value);
 int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int out_ch, int conv, float wn_eps,
                     float bn_eps, nfb_stream_t stream);
 /* params_out (B, out_ch, h, w) = ConvNet(z1).  mode = NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL: `src` is the coupling's

@@ -42,11 +42,13 @@ _SIGNATURES = {
     'nfb_logit_inv': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_invconv1x1_weight': [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     'nfb_invconv1x1_apply': [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
+    'nfb_actnorm_invconv_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'nfb_squeeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nfb_unsqueeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nfb_gauss_nll': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_weight_norm': [_P, _P, _P, _I, _I, _F, _P],
     'nfb_resnet_pack_size': [_I, _I, _I],
+    'nfb_set_tuning': [_I, _I],
     'nfb_resnet_pack': [_P, _P, _I, _I, _I, _F, _F, _P],
     'nfb_convnet_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

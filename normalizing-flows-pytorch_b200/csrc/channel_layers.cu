@@ -152,9 +152,12 @@ struct LogitRow {
     __device__ __forceinline__ float one(float& x) const {
         if (!INV) {
             x = fminf(fmaxf(x, lo), hi);                     // modules.py:147
-            const float y = logf(__fdiv_rn(x, __fsub_rn(1.f, x)));  // torch.logit
-            x = y;
-            return -log_dsigmoid_f(y);                        // modules.py:29-32
+            // logit(x) = log x - log(1-x) and -(y - 2 softplus(y)) = -(log x + log(1-x)) exactly (softplus(logit x) =
+            // -log(1-x)); two logf instead of div + logf + expf + log1pf.  |error| <= 2 ulp of max|log|, i.e. the same
+            // order as the reference's own fp32 rounding (modules.py:29-32,148-150).
+            const float l0 = logf(x), l1 = logf(__fsub_rn(1.f, x));
+            x = __fsub_rn(l0, l1);
+            return -__fadd_rn(l0, l1);
         }
         const float ld = log_dsigmoid_f(x);                   // modules.py:153
         x = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));         // torch.sigmoid

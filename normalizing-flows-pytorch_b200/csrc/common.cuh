@@ -182,8 +182,29 @@ __global__ void __launch_bounds__(256) rows_small_kernel(F f, const float* ldj_i
     if (live && gl == 0 && ldj_out) ldj_out[row] = ldj_in[row] + f.finish(acc);
 }
 
+// rows_warp: one WARP per row, lanes stride over the items, shuffle reduce -- no block barrier at all.  Used when
+// the batch alone fills the machine (streaming sizes): resident warps are then limited only by registers.
+template <class F>
+__global__ void __launch_bounds__(256, 4) rows_warp_kernel(F f, const float* ldj_in, float* ldj_out, int B) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+        float acc = 0.f;
+        for (int it = lane; it < f.items; it += 32) acc += f(row, it);
+        acc = warp_sum(acc);
+        if (lane == 0 && ldj_out) ldj_out[row] = ldj_in[row] + f.finish(acc);
+    }
+}
+
 template <class F>
 inline int launch_rows(const F& f, const float* ldj_in, float* ldj_out, int B, cudaStream_t st) {
+    if (f.items > 32 && f.items <= 4096 && static_cast<long long>(B) * 32 >= static_cast<long long>(kSMs) * 2048) {
+        const int rows_per_block = 8;
+        long long grid = (static_cast<long long>(B) + rows_per_block - 1) / rows_per_block;
+        if (grid > kSMs * 64) grid = kSMs * 64;
+        rows_warp_kernel<F><<<static_cast<int>(grid), 32 * rows_per_block, 0, st>>>(f, ldj_in, ldj_out, B);
+        return launch_status();
+    }
     if (f.items > 32) {
         int threads = f.items >= 512 ? 512 : ((f.items + 31) / 32) * 32;
         // a sample needing several passes is better served by 256 threads x more CTAs per SM

@@ -110,15 +110,34 @@ __host__ __device__ inline PackLayout pack_layout(int Cin, int Cout, int kk) {
 // ---------------------------------------------------------------------------------------------------------
 // fused ConvNet
 // ---------------------------------------------------------------------------------------------------------
-// 8 output channels x 4 pixels per thread, one 3x3 layer over CI input channels held in shared memory.
-template <int H, int W>
-__device__ __forceinline__ void conv3x3_acc(float (&acc)[8][4], const float* __restrict__ a_base /* bufA + sample base */,
+// OCT output channels x 4 pixels per thread, one 3x3 layer over CI input channels held in shared memory.
+template <int OCT>
+__device__ __forceinline__ void load_w(float (&wv)[OCT], const float* __restrict__ p) {
+    if (OCT == 8) {
+        const float4 a = ld4(p), b = ld4(p + 4);
+        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+        wv[4 % OCT] = b.x; wv[5 % OCT] = b.y; wv[6 % OCT] = b.z; wv[7 % OCT] = b.w;
+    } else if (OCT == 4) {
+        const float4 a = ld4(p);
+        wv[0] = a.x; wv[1] = a.y; wv[2 % OCT] = a.z; wv[3 % OCT] = a.w;
+    } else if (OCT == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(p);
+        wv[0] = a.x; wv[1 % OCT] = a.y;
+    } else {
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) wv[o] = p[o];
+    }
+}
+
+template <int H, int W, int OCT>
+__device__ __forceinline__ void conv3x3_acc(float (&acc)[OCT][4], const float* __restrict__ a_base /* bufA + sample base */,
                                             int chs, const float* __restrict__ wst /* [ci][9][32] */, int CI, int og,
                                             int y, int x0) {
     const bool left_edge = (x0 == 0), right_edge = (x0 + 4 == W);
+#pragma unroll 2
     for (int ci = 0; ci < CI; ++ci) {
         const float* a = a_base + ci * chs + y * W + x0;  // padded row index y+ky, ky = 0..2
-        const float* wrow = wst + ci * 9 * kF + og * 8;
+        const float* wrow = wst + ci * 9 * kF + og * OCT;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const float4 c = ld4(a + ky * W);
@@ -132,11 +151,10 @@ __device__ __forceinline__ void conv3x3_acc(float (&acc)[8][4], const float* __r
             const float av[6] = {l, c.x, c.y, c.z, c.w, r};
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4 w0 = ld4(wrow + (ky * 3 + kx) * kF);
-                const float4 w1 = ld4(wrow + (ky * 3 + kx) * kF + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                float wv[OCT];
+                load_w<OCT>(wv, wrow + (ky * 3 + kx) * kF);
 #pragma unroll
-                for (int o = 0; o < 8; ++o)
+                for (int o = 0; o < OCT; ++o)
 #pragma unroll
                     for (int p = 0; p < 4; ++p) acc[o][p] = fmaf(wv[o], av[p + kx], acc[o][p]);
             }
@@ -145,12 +163,13 @@ __device__ __forceinline__ void conv3x3_acc(float (&acc)[8][4], const float* __r
 }
 
 // MODE: NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL gather z1 from the coupling's z; MODE < 0: x is the (B,Cin,H,W) input.
-template <int H, int W, int NT, int MODE>
+template <int H, int W, int NT, int OCT, int MODE>
 __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
                                                           const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
                                                           int B) {
     constexpr int PGS = H * W / 4;         // pixel groups per sample
-    constexpr int NPG = NT / 4;            // pixel groups per CTA
+    constexpr int NOG = kF / OCT;          // groups of output channels
+    constexpr int NPG = NT / NOG;          // pixel groups per CTA
     constexpr int S = NPG / PGS;           // samples per CTA
     static_assert(S >= 1 && S * PGS == NPG, "tile must hold whole samples");
     constexpr int CHS = S * (H + 2) * W;   // channel stride of bufA (rows 0 and H+1 of every sample stay zero)
@@ -208,10 +227,10 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
     for (int i = t; i < kF * CHS; i += NT) bufA[i] = 0.f;  // includes the zero halo rows
     __syncthreads();
 
-    float xres[8][4];  // residual stream: this thread's 8 channels x 4 pixels
-    float acc[8][4];
+    float xres[OCT][4];  // residual stream: this thread's OCT channels x 4 pixels
+    float acc[OCT][4];
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
+    for (int o = 0; o < OCT; ++o)
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
 
@@ -235,21 +254,21 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
         }
         const float* w = acquire();
         prefetch_stage(++stage);
-        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, CI, og, y, x0);
+        conv3x3_acc<H, W, OCT>(acc, bufA + sbase, CHS, w, CI, og, y, x0);
     }
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        const float bias = __ldg(pk + L.b0 + og * 8 + o);
+    for (int o = 0; o < OCT; ++o) {
+        const float bias = __ldg(pk + L.b0 + og * OCT + o);
 #pragma unroll
         for (int p = 0; p < 4; ++p) xres[o][p] = acc[o][p] + bias;
     }
 
     // write relu(scale*v + shift) of this thread's tile into bufA (after everyone finished reading it)
-    auto store_act = [&](const float (&v)[8][4], const float* sc_sh) {
+    auto store_act = [&](const float (&v)[OCT][4], const float* sc_sh) {
         __syncthreads();
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int ch = og * 8 + o;
+        for (int o = 0; o < OCT; ++o) {
+            const int ch = og * OCT + o;
             const float sc = sc_sh ? __ldg(sc_sh + ch) : 1.f, sh = sc_sh ? __ldg(sc_sh + kF + ch) : 0.f;
             float4 q;
             q.x = fmaxf(fmaf(v[o][0], sc, sh), 0.f);
@@ -267,13 +286,13 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
         const float* w = acquire();
         prefetch_stage(++stage);
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
+        for (int o = 0; o < OCT; ++o)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
-        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
+        conv3x3_acc<H, W, OCT>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const float bias = __ldg(pk + L.b1[blk] + og * 8 + o);  // second BN folded into (w1, b1)
+        for (int o = 0; o < OCT; ++o) {
+            const float bias = __ldg(pk + L.b1[blk] + og * OCT + o);  // second BN folded into (w1, b1)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[o][p] += bias;
         }
@@ -281,13 +300,13 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
         w = acquire();
         prefetch_stage(++stage);
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
+        for (int o = 0; o < OCT; ++o)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
-        conv3x3_acc<H, W>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
+        conv3x3_acc<H, W, OCT>(acc, bufA + sbase, CHS, w, kF, og, y, x0);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const float bias = __ldg(pk + L.b2[blk] + og * 8 + o);
+        for (int o = 0; o < OCT; ++o) {
+            const float bias = __ldg(pk + L.b2[blk] + og * OCT + o);
 #pragma unroll
             for (int p = 0; p < 4; ++p) xres[o][p] += acc[o][p] + bias;
         }
@@ -299,17 +318,17 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
         const float* w = acquire();  // [32 ic][32 oc]
         prefetch_stage(++stage);
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
+        for (int o = 0; o < OCT; ++o)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
         const float* a = bufA + sbase + (y + 1) * W + x0;
 #pragma unroll 4
         for (int ci = 0; ci < kF; ++ci) {
             const float4 v = ld4(a + ci * CHS);
-            const float4 w0 = ld4(w + ci * kF + og * 8), w1 = ld4(w + ci * kF + og * 8 + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float wv[OCT];
+            load_w<OCT>(wv, w + ci * kF + og * OCT);
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
+            for (int o = 0; o < OCT; ++o) {
                 acc[o][0] = fmaf(wv[o], v.x, acc[o][0]);
                 acc[o][1] = fmaf(wv[o], v.y, acc[o][1]);
                 acc[o][2] = fmaf(wv[o], v.z, acc[o][2]);
@@ -318,8 +337,8 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
         }
         if (valid) {
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const int oc = c * kF + og * 8 + o;
+            for (int o = 0; o < OCT; ++o) {
+                const int oc = c * kF + og * OCT + o;
                 if (oc < Cout) {
                     const float bias = __ldg(pk + L.bout + oc);
                     st4(out + ((static_cast<size_t>(b) * Cout + oc) * H + y) * W + x0,
@@ -330,12 +349,12 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
     }
 }
 
-template <int H, int W, int NT, int MODE>
+template <int H, int W, int NT, int OCT, int MODE>
 static int launch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                           cudaStream_t st) {
-    constexpr int S = (NT / 4) / (H * W / 4);
+    constexpr int S = (NT / (kF / OCT)) / (H * W / 4);
     constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 2 * kWStage) * sizeof(float);
-    auto kern = convnet_fused_kernel<H, W, NT, MODE>;
+    auto kern = convnet_fused_kernel<H, W, NT, OCT, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -345,12 +364,36 @@ static int launch_convnet(const float* zsrc, float* out, const float* pk, const 
     return launch_status();
 }
 
+int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // runtime variant selection (nfb_set_tuning); 0 = default
+
 template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                             int h, int w, cudaStream_t st) {
-    if (h == 16 && w == 16) return launch_convnet<16, 16, 256, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
-    if (h == 8 && w == 8) return launch_convnet<8, 8, 64, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
-    if (h == 4 && w == 4) return launch_convnet<4, 4, 32, MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
+#define NFB_CONV(H_, W_, NT_, OCT_) return launch_convnet<H_, W_, NT_, OCT_, MODE>(zsrc, out, pk, g, Cin, Cout, B, st)
+    if (h == 16 && w == 16) {
+        switch (g_tune[0]) {
+            case 1: NFB_CONV(16, 16, 512, 4);
+            default: NFB_CONV(16, 16, 256, 8);
+        }
+    }
+    if (h == 8 && w == 8) {
+        switch (g_tune[1]) {
+            case 1: NFB_CONV(8, 8, 64, 8);
+            case 2: NFB_CONV(8, 8, 256, 2);
+            case 3: NFB_CONV(8, 8, 256, 4);
+            default: NFB_CONV(8, 8, 128, 4);
+        }
+    }
+    if (h == 4 && w == 4) {
+        switch (g_tune[2]) {
+            case 1: NFB_CONV(4, 4, 32, 8);
+            case 2: NFB_CONV(4, 4, 64, 2);
+            case 3: NFB_CONV(4, 4, 128, 4);
+            case 4: NFB_CONV(4, 4, 256, 2);
+            default: NFB_CONV(4, 4, 128, 2);
+        }
+    }
+#undef NFB_CONV
     return NFB_ERR_UNSUPPORTED;
 }
 
@@ -423,6 +466,12 @@ __global__ void __launch_bounds__(128) mlp_fused_kernel(const float* __restrict_
 }  // namespace nfb
 
 using namespace nfb;
+
+extern "C" int nfb_set_tuning(int key, int value) {
+    if (key < 0 || key >= 8) return NFB_ERR_SHAPE;
+    g_tune[key] = value;
+    return NFB_OK;
+}
 
 extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;

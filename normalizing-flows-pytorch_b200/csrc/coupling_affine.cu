@@ -42,6 +42,8 @@ struct AffineVec {
     SplitGeom g;
     int items;
     bool inplace;
+    bool pow2;          // checkerboard: h*w/4 and w/4 are powers of two -> shifts instead of divisions
+    int sh_ipl, sh_wq;
 
     __device__ __forceinline__ float finish(float acc) const { return INV ? -acc : acc; }
 
@@ -73,24 +75,31 @@ struct AffineVec {
             else        acc += affine_vec4<INV>(v0.y, v0.w, v1.y, v1.w, t, s, a, b);
             st4(zo + 8 * it, v0); st4(zo + 8 * it + 4, v1);
         } else {
-            // checkerboard: 8 consecutive x of one (c, y) line; even x -> squeezed channel k, odd x -> k+1
-            const int e0 = 8 * it;
-            const int c = e0 / g.HW;
-            const int r = e0 - c * g.HW;
-            const int y = r / g.W;
-            const int x0 = r - y * g.W;
-            const int k = 4 * c + 2 * (y & 1);
-            int me, mo;
-            const bool te = checker_block(g, k, me), to = checker_block(g, k + 1, mo);
-            float4 v0 = ld4(zr + e0), v1 = ld4(zr + e0 + 4);
-            const int sp = (y >> 1) * g.w + (x0 >> 1);
+            // checkerboard.  Items are ordered (c, dy, i, jb): item = 8 consecutive x (jb) of input line y = 2i+dy of
+            // channel c, so all items of one (c, dy) -- h*w/4 of them, >= a warp for 32x32 images -- share the two
+            // squeezed channels k = 4c+2dy (even x) and k+1 (odd x): the z0/z1 classification is warp-uniform and
+            // costs three compares instead of integer divisions.
+            const int wq = g.w >> 2;                 // items per line (W/8)
+            const int ipl = g.h * wq;                // items per (c, dy)
+            int cd, rem, i, jb;
+            if (pow2) { cd = it >> sh_ipl; rem = it & (ipl - 1); i = rem >> sh_wq; jb = rem & (wq - 1); }
+            else { cd = it / ipl; rem = it - cd * ipl; i = rem / wq; jb = rem - i * wq; }
+            const int k = 2 * cd;                    // 4c + 2dy
+            const int e0 = (cd >> 1) * g.HW + (2 * i + (cd & 1)) * g.W + 8 * jb;
+            const int qe = (k >= g.C) + (k >= 2 * g.C) + (k >= 3 * g.C);
+            const int qo = (k + 1 >= g.C) + (k + 1 >= 2 * g.C) + (k + 1 >= 3 * g.C);
+            const bool te = ((qe == 0 || qe == 3) ? 1 : 0) != g.odd, to = ((qo == 0 || qo == 3) ? 1 : 0) != g.odd;
+            const int me = (qe == 0) ? k : (qe == 3) ? k - 2 * g.C : k - g.C;
+            const int mo = (qo == 0) ? k + 1 : (qo == 3) ? k + 1 - 2 * g.C : k + 1 - g.C;
             const int hw = g.h * g.w;
-            float4 t_e, s_e, t_o, s_o;
+            const int sp = i * g.w + 4 * jb;
+            float4 v0, v1, t_e, s_e, t_o, s_o;
+            if (te || to || !inplace) { v0 = ld4(zr + e0); v1 = ld4(zr + e0 + 4); }
             if (te) { t_e = ldg4(pr + me * hw + sp); s_e = ldg4(pr + g.n0 + me * hw + sp); }
             if (to) { t_o = ldg4(pr + mo * hw + sp); s_o = ldg4(pr + g.n0 + mo * hw + sp); }
             if (te) acc += affine_vec4<INV>(v0.x, v0.z, v1.x, v1.z, t_e, s_e, a, b);
             if (to) acc += affine_vec4<INV>(v0.y, v0.w, v1.y, v1.w, t_o, s_o, a, b);
-            if (!inplace || te || to) { st4(zo + e0, v0); st4(zo + e0 + 4, v1); }
+            if (te || to || !inplace) { st4(zo + e0, v0); st4(zo + e0 + 4, v1); }
         }
         return acc;
     }
@@ -135,7 +144,15 @@ static int launch_affine(const float* z_in, float* z_out, const float* params, c
     else if (MODE == NFB_SPLIT_1D) { vec = vec && (g.D % 8 == 0); items = g.D / 8; }
     else                           { vec = vec && (g.W % 8 == 0); items = g.D / 8; }
     if (vec) {
-        AffineVec<MODE, INV> f{z_in, z_out, params, a, b, g, items, inplace};
+        AffineVec<MODE, INV> f{z_in, z_out, params, a, b, g, items, inplace, false, 0, 0};
+        if (MODE == NFB_SPLIT_CHECKER) {
+            const int wq = g.w / 4, ipl = g.h * wq;
+            auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+            auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+            f.pow2 = is_pow2(wq) && is_pow2(ipl);
+            f.sh_ipl = lg(ipl);
+            f.sh_wq = lg(wq);
+        }
         return launch_rows(f, ldj_in, ldj_out, g.B, st);
     }
     AffineScalar<MODE, INV> f{z_in, z_out, params, a, b, g, g.D, inplace};

@@ -84,12 +84,34 @@ __global__ void __launch_bounds__(256) invconv_apply_scalar(const float* __restr
 }
 
 // ---- apply: tiled kernel.  CTA = one sample x TP pixels; thread = 4 pixels x OCG output channels ----------
-// shared: Mt[ci][co] (transposed so OCG consecutive co are one vector load), zs[ci][TP]
+// shared: Mt[ci][co] (transposed so OCG consecutive co are one vector load), zs[ci][TP].
+// ACTNORM: the preceding ActNorm layer (modules.py:246-249) is applied while z is staged into shared memory,
+// (z - bias)/exp(log_scale) and its log-det term first -- bit-identical to running the two layers back to back.
 template <int OCG>
+__device__ __forceinline__ void load_m(float (&m)[OCG], const float* p) {
+    if (OCG == 8) {
+        const float4 a = ld4(p), b = ld4(p + 4);
+        m[0] = a.x; m[1 % OCG] = a.y; m[2 % OCG] = a.z; m[3 % OCG] = a.w;
+        m[4 % OCG] = b.x; m[5 % OCG] = b.y; m[6 % OCG] = b.z; m[7 % OCG] = b.w;
+    } else if (OCG == 4) {
+        const float4 a = ld4(p);
+        m[0] = a.x; m[1 % OCG] = a.y; m[2 % OCG] = a.z; m[3 % OCG] = a.w;
+    } else if (OCG == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(p);
+        m[0] = a.x; m[1 % OCG] = a.y;
+    } else {
+#pragma unroll
+        for (int o = 0; o < OCG; ++o) m[o] = p[o];
+    }
+}
+
+template <int OCG, bool ACTNORM>
 __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restrict__ zin, float* __restrict__ zout,
                                                           const float* ldj_in, float* ldj_out,
                                                           const float* __restrict__ M, const float* __restrict__ log_s,
-                                                          float sign, int B, int C, int HW, int TP) {
+                                                          const float* __restrict__ an_log_scale,
+                                                          const float* __restrict__ an_bias, float sign, int B, int C,
+                                                          int HW, int TP) {
     extern __shared__ __align__(16) float sm[];
     float* Mt = sm;                          // C*C
     float* zs = sm + ((C * C + 3) & ~3);     // C*TP, 16-byte aligned
@@ -97,21 +119,38 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
     const int p0 = blockIdx.x * TP;
     const int tp = (HW - p0) < TP ? (HW - p0) : TP;  // multiple of 4
 
+    // Mt[ci][co] = M[co][ci]: contiguous (conflict-free) shared stores, strided reads of the small L1-resident matrix
     for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
-        const int co = i / C, ci = i - co * C;
-        Mt[ci * C + co] = __ldg(M + i);
+        const int ci = i / C, co = i - ci * C;
+        Mt[i] = __ldg(M + co * C + ci);
     }
     const float* zb = zin + (static_cast<size_t>(b) * C) * HW + p0;
     const int tpv = tp >> 2;
     for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
         const int ci = i / tpv, pv = i - ci * tpv;
-        st4(zs + ci * TP + 4 * pv, ldg4(zb + static_cast<size_t>(ci) * HW + 4 * pv));
+        float4 v = ldg4(zb + static_cast<size_t>(ci) * HW + 4 * pv);
+        if (ACTNORM) {
+            const float e = expf(__ldg(an_log_scale + ci)), bi = __ldg(an_bias + ci);
+            v.x = __fdiv_rn(__fsub_rn(v.x, bi), e);
+            v.y = __fdiv_rn(__fsub_rn(v.y, bi), e);
+            v.z = __fdiv_rn(__fsub_rn(v.z, bi), e);
+            v.w = __fdiv_rn(__fsub_rn(v.w, bi), e);
+        }
+        st4(zs + ci * TP + 4 * pv, v);
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
-        float part = 0.f;
-        for (int c = threadIdx.x; c < C; c += 32) part += __ldg(log_s + c);
+        float part = 0.f, an = 0.f;
+        for (int c = threadIdx.x; c < C; c += 32) {
+            part += __ldg(log_s + c);
+            if (ACTNORM) an -= __ldg(an_log_scale + c);
+        }
         part = warp_sum(part);
-        if (threadIdx.x == 0) ldj_out[b] = __fadd_rn(ldj_in[b], __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+        if (ACTNORM) an = warp_sum(an);
+        if (threadIdx.x == 0) {
+            float l = ldj_in[b];
+            if (ACTNORM) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+            ldj_out[b] = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+        }
     }
     __syncthreads();
 
@@ -127,8 +166,7 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
         for (int ci = 0; ci < C; ++ci) {
             const float4 z = ld4(zcol + ci * TP);
             float m[OCG];
-#pragma unroll
-            for (int o = 0; o < OCG; ++o) m[o] = mrow[ci * C + o];
+            load_m<OCG>(m, mrow + ci * C);
 #pragma unroll
             for (int o = 0; o < OCG; ++o) {
                 acc[o][0] = fmaf(m[o], z.x, acc[o][0]);
@@ -143,9 +181,10 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
     }
 }
 
-template <int OCG>
+template <int OCG, bool ACTNORM>
 static int launch_tiled(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
-                        const float* log_s, float sign, int B, int C, int HW, cudaStream_t st) {
+                        const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
+                        cudaStream_t st) {
     // pixel tile: whole sample if it fits, else the largest multiple of 4 that keeps shared memory <= ~96 KB
     int TP = HW;
     const size_t budget = 96 * 1024;
@@ -153,14 +192,30 @@ static int launch_tiled(const float* zin, float* zout, const float* ldj_in, floa
     while ((mt + static_cast<size_t>(C) * TP) * 4 > budget && TP > 16) TP = ((TP / 2 + 3) / 4) * 4;
     const size_t smem = (mt + static_cast<size_t>(C) * TP) * 4;
     if (smem > 200 * 1024) return -100;  // caller falls back to the scalar kernel
-    auto kern = invconv_apply_tiled<OCG>;
+    auto kern = invconv_apply_tiled<OCG, ACTNORM>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int work = (C / OCG) * (TP / 4);
     int threads = work >= 512 ? 512 : ((work + 31) / 32) * 32;
     if (threads < 64) threads = 64;
     dim3 grid((HW + TP - 1) / TP, B);
-    kern<<<grid, threads, smem, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, sign, B, C, HW, TP);
+    kern<<<grid, threads, smem, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, TP);
     return launch_status();
+}
+
+template <bool ACTNORM>
+static int apply_dispatch(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
+                          const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
+                          cudaStream_t st) {
+    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && B <= 65535) {
+        int rc;
+        if (C % 8 == 0 && C >= 96) rc = launch_tiled<8, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        else if (C % 4 == 0) rc = launch_tiled<4, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        else if (C % 3 == 0) rc = launch_tiled<3, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        else if (C % 2 == 0) rc = launch_tiled<2, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        else rc = launch_tiled<1, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        if (rc != -100) return rc;
+    }
+    return -100;
 }
 
 }  // namespace nfb
@@ -183,15 +238,8 @@ extern "C" int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && B <= 65535) {
-        int rc = -100;
-        if (C % 8 == 0) rc = launch_tiled<8>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
-        else if (C % 4 == 0) rc = launch_tiled<4>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
-        else if (C % 3 == 0) rc = launch_tiled<3>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
-        else if (C % 2 == 0) rc = launch_tiled<2>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
-        else rc = launch_tiled<1>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW, st);
-        if (rc != -100) return rc;
-    }
+    const int rc = apply_dispatch<false>(z_in, z_out, ldj_in, ldj_out, M, log_s, nullptr, nullptr, sign, B, C, HW, st);
+    if (rc != -100) return rc;
     const long long total = static_cast<long long>(B) * C * HW;
     long long blocks = (total + 255) / 256;
     const long long need = (B + 255) / 256;
@@ -199,4 +247,15 @@ extern "C" int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float
     if (blocks < need) blocks = need;
     invconv_apply_scalar<<<static_cast<int>(blocks), 256, 0, st>>>(z_in, z_out, ldj_in, ldj_out, M, log_s, sign, B, C, HW);
     return launch_status();
+}
+
+extern "C" int nfb_actnorm_invconv_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out,
+                                       const float* log_scale, const float* bias, const float* W, const float* log_s,
+                                       int B, int C, int HW, nfb_stream_t stream) {
+    if (!z_in || !z_out || !ldj_in || !ldj_out || !log_scale || !bias || !W || !log_s) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
+    const int rc = apply_dispatch<true>(z_in, z_out, ldj_in, ldj_out, W, log_s, log_scale, bias, 1.f, B, C, HW,
+                                        as_stream(stream));
+    return rc == -100 ? NFB_ERR_UNSUPPORTED : rc;  // caller runs the two layers separately for odd shapes
 }

@@ -59,9 +59,15 @@ class _ResNetConditioner(nn.Module):
             ts += [m.weight, m.bias, m.running_mean, m.running_var]
         return ts, wn[0].eps, bn[0].eps
 
+    def _apply(self, fn, *a, **k):  # .to() / .cuda(): storage moves, drop every cache
+        self._pack_key = self._ts = None
+        return super()._apply(fn, *a, **k)
+
     def packed(self):
-        ts, wn_eps, bn_eps = self._tensors()
-        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if getattr(self, '_ts', None) is None:
+            self._ts = self._tensors()
+        ts, wn_eps, bn_eps = self._ts
+        key = tuple([t._version for t in ts])  # in-place updates (optimizer, load_state_dict) bump _version
         if key != getattr(self, '_pack_key', None):
             if len(self.mid_block) != 2 or self.base_filters != 32:
                 raise NotImplementedError('fused conditioner kernel is built for base_filters=32, n_blocks=2 '

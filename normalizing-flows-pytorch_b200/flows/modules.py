@@ -195,16 +195,44 @@ class InvertibleConv1x1(nn.Module):
     inverse = backward
 
 
+def _actnorm_invconv(an, conv, z, log_df_dz):
+    """ActNorm.forward + InvertibleConv1x1.forward as one launch; None if the shape needs the separate kernels."""
+    z, log_df_dz = L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz')
+    B, C, HW = _bchw(z)
+    out = torch.empty_like(z)
+    rc = L.lib().nfb_actnorm_invconv_fwd(L.ptr(z), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz),
+                                         L.ptr(an.log_scale.data), L.ptr(an.bias.data), L.ptr(conv.matrices()[0]),
+                                         L.ptr(conv.log_s.data), B, C, HW, L.stream())
+    if rc == L.ERR_UNSUPPORTED:
+        return None
+    L.check(rc)
+    return out, log_df_dz
+
+
 class Compose(nn.Module):
     """modules.py:325-339: sequential / reversed application."""
+
+    fuse_steps = True  # set False to run every layer as its own kernel
 
     def __init__(self, layers):
         super().__init__()
         self.layers = nn.ModuleList(layers)
 
     def forward(self, z, log_df_dz):
-        for layer in self.layers:
+        layers = self.layers
+        n, i = len(layers), 0
+        while i < n:
+            layer = layers[i]
+            # peephole: an initialised ActNorm followed by the 1x1 convolution runs as one kernel (same arithmetic)
+            if (i + 1 < n and type(layer) is ActNorm and layer.initialized and type(layers[i + 1]) is InvertibleConv1x1
+                    and self.fuse_steps):
+                out = _actnorm_invconv(layer, layers[i + 1], z, log_df_dz)
+                if out is not None:
+                    z, log_df_dz = out
+                    i += 2
+                    continue
             z, log_df_dz = layer(z, log_df_dz)
+            i += 1
         return z, log_df_dz
 
     def backward(self, z, log_df_dz):

@@ -391,3 +391,42 @@ def test_conditioner_gathers_z1_in_kernel(dims, masking, odd):
     _, z1 = coupling_split(z, cpl.mode, cpl.odd, want_z0=False)
     p2 = cpl.net(z1)
     assert p1 is not None and torch.equal(p1, p2)
+
+
+def test_fused_actnorm_invconv_is_bit_identical():
+    """Compose's ActNorm+InvertibleConv1x1 peephole must give exactly what the two layers give separately."""
+    n = nfb()
+    torch.manual_seed(2)
+    for dims in [(3, 32, 32), (12, 16, 16), (48, 8, 8), (192, 8, 8), (6, )]:
+        an = n.flows.ActNorm(dims)
+        conv = n.flows.InvertibleConv1x1(dims[0])
+        perturb_(an, 1)
+        perturb_(conv, 2)
+        an.initialized = True
+        comp = n.flows.Compose([an, conv]).to(DEV)
+        x = torch.randn((5, ) + dims, device=DEV)
+        l0 = torch.randn(5, device=DEV)
+        z1, l1 = comp(x, l0.clone())
+        comp.fuse_steps = False
+        z2, l2 = comp(x, l0.clone())
+        assert torch.equal(z1, z2) and torch.equal(l1, l2), dims
+
+
+@pytest.mark.parametrize('key,values,cin,cout,hw', [(0, (0, 1), 6, 12, 16), (1, (0, 1, 2, 3), 24, 48, 8),
+                                                    (2, (0, 1, 2, 3, 4), 96, 192, 4)])
+def test_convnet_variants_agree(key, values, cin, cout, hw):
+    """All thread-tile variants of the fused ConvNet kernel compute the same sums in the same order."""
+    import nfb200._lib as L
+    F = nfb().flows
+    torch.manual_seed(0)
+    net = F.ConvNet(cin, cout).to(DEV).eval()
+    x = torch.randn(37, cin, hw, hw, device=DEV)
+    outs = []
+    try:
+        for v in values:
+            L.check(L.lib().nfb_set_tuning(key, v))
+            outs.append(net(x))
+    finally:
+        L.lib().nfb_set_tuning(key, 0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
