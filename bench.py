@@ -194,35 +194,106 @@ def time_kernel_stream(fn, iters, flush=None):
     return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
 
 
+def _ncu_traffic(key):
+    """dram__bytes_read+write per launch from the committed ncu --set full summary (profiles/ncu_summary.json)."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
+    try:
+        with open(p) as f:
+            return json.load(f).get(key, {}).get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        return None
+
+
 def coupling_roofline(peaks):
     """Streaming-size run of the fused affine coupling + log-det kernel (the kernel BASELINE.json's target names):
-    inputs 3 x 201 MB > L2, L2 flushed between launches, CUDA events on the launching stream."""
+    z, params and out are 201 MB each (604 MB > 126 MB L2), L2 flushed between launches, CUDA events on the
+    launching stream.  Headline = checkerboard split at the cfg-2 first-level shape; the other splits ride along."""
     import nfb200._lib as L
-    dims, B = (3, 32, 32), 16384
-    D = 3 * 32 * 32
-    z = torch.randn((B, ) + dims, device='cuda')
-    params = torch.randn((B, ) + dims, device='cuda')
+    B, D = 16384, 3072
+    z = torch.randn(B, D, device='cuda')
+    params = torch.randn(B, D, device='cuda')
     out = torch.empty_like(z)
     ldj = torch.zeros(B, device='cuda')
     a = torch.tensor([0.3], device='cuda')
     b = torch.tensor([0.01], device='cuda')
     flush = torch.empty(L2_BYTES * 2 // 4, device='cuda', dtype=torch.float32)
     st = L.stream()
-
-    def run():
-        L.check(L.lib().nfb_affine_coupling_fwd(z.data_ptr(), out.data_ptr(), params.data_ptr(), ldj.data_ptr(),
-                                                ldj.data_ptr(), a.data_ptr(), b.data_ptr(), B, 3, 32, 32,
-                                                L.SPLIT_CHECKER, 0, st))
-    for _ in range(3):
-        run()
-    mean, med, best = time_kernel_stream(run, 20, flush)
     alg = (12 * D + 8) * B  # z in 4D + (t, s) 4D + z out 4D + log-det read-modify-write
-    achieved = alg / (med * 1e-3) / 1e9
     peak = peaks['hbm_gbs']
-    return {'kernel': 'affine_coupling_fwd (checkerboard 3x32x32, B=16384, out-of-place)', 'bound': 'hbm',
-            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-            'ms_per_launch': med, 'alg_bytes_per_launch': alg, 'peak_source': peaks['source'],
-            'l2': 'flushed between launches (252 MB write); inputs 604 MB > 126 MB L2'}
+    res = {}
+    for name, (C, H, W, mode) in {'checkerboard 3x32x32': (3, 32, 32, L.SPLIT_CHECKER),
+                                  'channelwise 12x16x16': (12, 16, 16, L.SPLIT_CHANNEL),
+                                  '1-D 3072': (3072, 1, 1, L.SPLIT_1D)}.items():
+        def run():
+            L.check(L.lib().nfb_affine_coupling_fwd(z.data_ptr(), out.data_ptr(), params.data_ptr(), ldj.data_ptr(),
+                                                    ldj.data_ptr(), a.data_ptr(), b.data_ptr(), B, C, H, W, mode, 0, st))
+        for _ in range(3):
+            run()
+        mean, med, best = time_kernel_stream(run, 20, flush)
+        res[name] = {'ms_per_launch': med, 'achieved': alg / (med * 1e-3) / 1e9}
+    head = res['checkerboard 3x32x32']
+    return {'kernel': 'nfb_affine_coupling_fwd = rows_warp_kernel<AffineVec<checker>> (split-gather + affine + merge-scatter '
+                      '+ per-sample log-det), 3x32x32, B=16384, out-of-place',
+            'bound': 'hbm', 'achieved': head['achieved'], 'peak': peak, 'unit': 'GB/s', 'frac': head['achieved'] / peak,
+            'traffic': _ncu_traffic('affine_coupling_stream'), 'ms_per_launch': head['ms_per_launch'],
+            'alg_bytes_per_launch': alg, 'peak_source': peaks['source'],
+            'l2': 'flushed between launches (252 MB write); inputs 604 MB > 126 MB L2',
+            'other_splits': {k: {'achieved': v['achieved'], 'frac': v['achieved'] / peak} for k, v in res.items()
+                             if k != 'checkerboard 3x32x32'}}
+
+
+def graph_time_us(fn, per_graph=20, iters=10):
+    """median device time of one fn() in us: per_graph launches captured in a CUDA graph, events around replays."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(per_graph):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for e0, e1 in ev:
+        e0.record()
+        g.replay()
+        e1.record()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    return ts[len(ts) // 2] * 1e3 / per_graph
+
+
+def dominant_kernel_probe(net, batch, clocks):
+    """The kernel with the largest share of the step (profiles/: ~80 % for glow32): the fused ConvNet conditioner.
+    It is FP32-FFMA bound (split-precision tensor-core math is future work), so its ceiling is the FP32 pipe:
+    148 SMs x 128 FMA/clk x 2 x SM clock.  Timed live, CUDA-graph replay of 20 back-to-back launches."""
+    import nfb200
+    from nfb200.flows.coupling import AffineCoupling
+    seen, out = set(), []
+    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    for m in net.modules():
+        if not isinstance(m, AffineCoupling) or len(m.dims) != 3:
+            continue
+        C, H, W = m.dims
+        h, w = (H // 2, W // 2) if m.mode == nfb200._lib.SPLIT_CHECKER else (H, W)
+        key = (m.net.in_channels, m.net.out_channels, h, w)
+        if key in seen:
+            continue
+        seen.add(key)
+        z = torch.randn((batch, ) + tuple(m.dims), device='cuda')
+        if m.net.forward_from_z(z, m.mode, m.odd) is None:
+            continue
+        us = graph_time_us(lambda: m.net.forward_from_z(z, m.mode, m.odd))
+        mac = h * w * (key[0] * 288 + 4 * 9216 + 32 * key[1])
+        tf = 2 * mac * batch / us * 1e-6
+        out.append({'kernel': 'nfb_convnet_fwd %dx%d in=%d out=%d' % (h, w, key[0], key[1]), 'us_per_launch': us,
+                    'achieved': tf, 'unit': 'TFLOP/s', 'bound': 'fp32-ffma', 'peak': fp32_peak, 'frac': tf / fp32_peak})
+    return out
 
 
 def load_peaks():
@@ -367,11 +438,16 @@ def run_nfb200(args, rank, world, local_rank):
         return
 
     peaks = load_peaks()
-    roof = None
+    roof, dom = None, None
     try:
         roof = coupling_roofline(peaks)
     except Exception as e:  # the roofline probe must never take the bench line down
         roof = {'error': repr(e)}
+    try:
+        with torch.no_grad():
+            dom = dominant_kernel_probe(net, batch, clocks)
+    except Exception as e:
+        dom = {'error': repr(e)}
 
     # ---- CPU baseline on the box's host cores: oracle port, bounded sample ---------------------------------
     threads = os.cpu_count() or 1
@@ -400,7 +476,7 @@ def run_nfb200(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'h2d_bytes_per_step': bytes_per_batch, 'd2h_bytes_per_step': 16 + 4 * batch},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        'clocks': clocks, 'roofline': roof, 'conditioner_kernels': dom, 'cpu_baseline': cpu,
         'bits_per_dim': {'gpu_global_batch': bpd_global, 'gpu_rank0_batch': bpd_local, 'gpu_on_cpu_sample': bpd_gpu_sample,
                          'cpu_oracle_on_sample': bpd_cpu,
                          'rel_err': abs(bpd_gpu_sample - bpd_cpu) / abs(bpd_cpu), 'tolerance': 1e-5},
