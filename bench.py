@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def time_kernel_stream(fn, iters, flush=None):
@@ -382,7 +382,7 @@ def run_nfb200(args, rank, world, local_rank):
             # make sure the clock sampler saw the load: keep the GPU busy a little longer (untimed)
             t_end = time.perf_counter() + 1.0
             while time.perf_counter() < t_end:
-                step(0)
+                graph.replay()  # local work only: no collective outside the steps every rank executes
             torch.cuda.synchronize()
         clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -481,10 +481,28 @@ def run_nfb200(args, rank, world, local_rank):
                          'cpu_oracle_on_sample': bpd_cpu,
                          'rel_err': abs(bpd_gpu_sample - bpd_cpu) / abs(bpd_cpu), 'tolerance': 1e-5},
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, library chatter) was
+    re-routed to stderr in main()."""
+    line = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C libraries (NCCL prints its version banner on stdout) now write to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -505,7 +523,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                timeout=datetime.timedelta(seconds=90))
     try:
         run_nfb200(args, rank, world, local_rank)
     finally:
