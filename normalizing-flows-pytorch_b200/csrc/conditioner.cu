@@ -12,19 +12,9 @@
 // the coupling's split addressing (no materialised split).  Arithmetic is FP32 FFMA: bits/dim parity at 1e-5 with a
 // reference noise floor of 2e-7 rules out single-pass TF32/BF16 tensor-core math; an error-compensated
 // tcgen05 path is the next step.
-#include "common.cuh"
+#include "conditioner.cuh"
 
 namespace nfb {
-
-constexpr int kF = 32;            // base_filters of every conditioner in the reference (modules.py:392,417)
-constexpr int kWStage = 9 * kF * kF;  // floats of one 32->32 3x3 layer
-
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // packing (once per weight update)
@@ -78,33 +68,6 @@ __global__ void pack_bn_kernel(const float* __restrict__ w, const float* __restr
         scale[c] = sc;
         shift[c] = b[c] - rm[c] * sc;
     }
-}
-
-// packed buffer offsets (in floats); every section is a multiple of 32 floats (128 B)
-struct PackLayout {
-    int w0, b0;
-    int bnA[2], w1[2], b1[2], w2[2], b2[2];
-    int bnO, wout, bout;
-    int total;
-};
-__host__ __device__ inline PackLayout pack_layout(int Cin, int Cout, int kk) {
-    PackLayout L;
-    const int CoutPad = (Cout + 31) & ~31;
-    int o = 0;
-    L.w0 = o; o += Cin * kk * kF;
-    L.b0 = o; o += kF;
-    for (int i = 0; i < 2; ++i) {
-        L.bnA[i] = o; o += 2 * kF;
-        L.w1[i] = o; o += kF * kk * kF;
-        L.b1[i] = o; o += kF;
-        L.w2[i] = o; o += kF * kk * kF;
-        L.b2[i] = o; o += kF;
-    }
-    L.bnO = o; o += 2 * kF;
-    L.wout = o; o += kF * CoutPad;
-    L.bout = o; o += CoutPad;
-    L.total = o;
-    return L;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -369,6 +332,10 @@ int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // runtime variant selection (nfb_set
 template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                             int h, int w, cudaStream_t st) {
+    if (g_tune[3] == 1) {  // tensor-core (tcgen05 3xTF32) path
+        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_layout(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, st);
+        if (rc != NFB_ERR_UNSUPPORTED) return rc;
+    }
 #define NFB_CONV(H_, W_, NT_, OCT_) return launch_convnet<H_, W_, NT_, OCT_, MODE>(zsrc, out, pk, g, Cin, Cout, B, st)
     if (h == 16 && w == 16) {
         switch (g_tune[0]) {
@@ -475,7 +442,9 @@ extern "C" int nfb_set_tuning(int key, int value) {
 
 extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
-    return pack_layout(in_ch, out_ch, conv ? 9 : 1).total;
+    if (!conv) return pack_layout(in_ch, out_ch, 1).total;
+    const TcLayout T = tc_layout(in_ch, out_ch);  // FFMA section followed by the tensor-core (3xTF32) section
+    return T.base + T.total;
 }
 
 extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, int out_ch, int conv, float wn_eps,
@@ -511,7 +480,9 @@ extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, 
         if ((rc = wn(2 + 2 * i, -1, packed + L.w2[i], packed + L.b2[i], kF, kF * kk, kF))) return rc;
     }
     if ((rc = bn(4, packed + L.bnO))) return rc;
-    return wn(5, -1, packed + L.wout, packed + L.bout, out_ch, kF, CoutPad);
+    if ((rc = wn(5, -1, packed + L.wout, packed + L.bout, out_ch, kF, CoutPad))) return rc;
+    if (!conv) return NFB_OK;
+    return pack_tc_launch(packed, packed + tc_layout(in_ch, out_ch).base, in_ch, out_ch, st);
 }
 
 extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,

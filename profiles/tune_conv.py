@@ -48,6 +48,11 @@ for key, values, cin, cout, hw in [(0, (0, 1), 6, 12, 16), (1, (0, 1, 2, 3), 24,
         print('convnet %dx%d cin=%d cout=%d B=%d variant %d: %8.1f us  %6.2f TFLOP/s' %
               (hw, hw, cin, cout, B, v, us, 2 * mac * B / us * 1e-6))
     L.lib().nfb_set_tuning(key, 0)
+    L.check(L.lib().nfb_set_tuning(3, 1))
+    us = timeit(lambda: net(x))
+    print('convnet %dx%d cin=%d cout=%d B=%d TENSOR-CORE (3xTF32): %8.1f us  %6.2f TFLOP/s (logical)' %
+          (hw, hw, cin, cout, B, us, 2 * mac * B / us * 1e-6))
+    L.lib().nfb_set_tuning(3, 0)
 
 # 1x1 conv (+ fused ActNorm) and the elementwise layers at the cfg-2 shapes (L2-resident working set)
 F = nfb200.flows

@@ -430,3 +430,35 @@ def test_convnet_variants_agree(key, values, cin, cout, hw):
         L.lib().nfb_set_tuning(key, 0)
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize('cin,cout,hw,B', [(6, 12, 16, 3), (24, 48, 8, 5), (96, 192, 4, 7), (6, 12, 16, 256),
+                                           (40, 70, 8, 2), (24, 48, 8, 256), (96, 192, 4, 256)])
+def test_convnet_tensor_core_path(cin, cout, hw, B):
+    """tcgen05 3xTF32 implicit-GEMM conditioner vs the FP32-FFMA kernel and the CPU oracle (same tolerance class)."""
+    import nfb200._lib as L
+    F = nfb().flows
+    torch.manual_seed(cin + hw)
+    net = F.ConvNet(cin, cout)
+    perturb_(net, 9)
+    net.eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(B, cin, hw, hw)
+    with torch.no_grad():
+        ref = O.resnet_conditioner(sd, '', x[:8])
+        ref64 = O.resnet_conditioner(O.to_dtype(sd, torch.float64), '', x[:8].double())
+    net.to(DEV)
+    ffma = net(x.to(DEV))
+    try:
+        L.check(L.lib().nfb_set_tuning(3, 1))
+        tc = net(x.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        L.lib().nfb_set_tuning(3, 0)
+    scale = max(1.0, float(ref.abs().max()))
+    e_tc = float((tc[:8].cpu().double() - ref64).abs().max())
+    e_ff = float((ffma[:8].cpu().double() - ref64).abs().max())
+    e_ref = float((ref.double() - ref64).abs().max())
+    print('tensor-core err vs fp64 %.3e | ffma %.3e | cpu fp32 %.3e | scale %.2f' % (e_tc, e_ff, e_ref, scale))
+    close(tc, ffma, rtol=2e-5, atol=4e-6 * scale, what='tensor-core vs ffma')
+    assert e_tc <= 8.0 * max(e_ref, e_ff) + 1e-6 * scale
