@@ -188,6 +188,16 @@ int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int o
  * conditioner input: 16x16, 8x8, 4x4 (else NFB_ERR_UNSUPPORTED). */
 int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
                     int odd, int in_ch, int out_ch, nfb_stream_t stream);
+/* One whole Glow flow step (glow.py:27-29) in ONE launch: ActNorm.forward (modules.py:246-250) ->
+ * InvertibleConv1x1.forward (modules.py:470-482, Wm = the matrix from nfb_invconv1x1_weight) -> AffineCoupling.forward
+ * (coupling.py:32-36,104-112) with its ConvNet conditioner (packed by nfb_resnet_pack).  The conditioner output never
+ * leaves shared memory.  z_out must not alias z_in.  NFB_ERR_UNSUPPORTED for conditioner sizes other than 16x16 / 8x8 /
+ * 4x4 or when one sample plus the C x C matrix exceeds the staging buffer: run the three layers separately. */
+int nfb_glow_step_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* an_log_scale,
+                      const float* an_bias, const float* Wm, const float* log_s, const float* packed,
+                      const float* s_log_scale, const float* s_bias, int B, int C, int H, int W, int mode, int odd,
+                      nfb_stream_t stream);
+
 /* params_out (B, out_ch) = MLP(z1).  mode = NFB_SPLIT_1D: src = z (B, C), z1 gathered (squeeze.py:64-72);
  * mode < 0: src = (B, in_ch). */
 int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd, int in_ch,

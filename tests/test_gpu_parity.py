@@ -407,7 +407,7 @@ def test_fused_actnorm_invconv_is_bit_identical():
         x = torch.randn((5, ) + dims, device=DEV)
         l0 = torch.randn(5, device=DEV)
         z1, l1 = comp(x, l0.clone())
-        comp.fuse_steps = False
+        comp.fuse_steps = 0
         z2, l2 = comp(x, l0.clone())
         assert torch.equal(z1, z2) and torch.equal(l1, l2), dims
 
@@ -462,3 +462,32 @@ def test_convnet_tensor_core_path(cin, cout, hw, B):
     print('tensor-core err vs fp64 %.3e | ffma %.3e | cpu fp32 %.3e | scale %.2f' % (e_tc, e_ff, e_ref, scale))
     close(tc, ffma, rtol=2e-5, atol=4e-6 * scale, what='tensor-core vs ffma')
     assert e_tc <= 8.0 * max(e_ref, e_ff) + 1e-6 * scale
+
+
+@pytest.mark.parametrize('dims,masking', [((3, 32, 32), 'checkerboard'), ((12, 16, 16), 'channelwise'),
+                                          ((12, 16, 16), 'checkerboard'), ((48, 8, 8), 'channelwise'),
+                                          ((48, 8, 8), 'checkerboard')])
+@pytest.mark.parametrize('odd', [False, True])
+@pytest.mark.parametrize('B', [3, 256])
+def test_fused_glow_step_matches_separate_layers(dims, masking, odd, B):
+    """One-launch flow step (ActNorm -> 1x1 conv -> AffineCoupling) vs the three layers run separately: z identical
+    except for the reduction order of the log-det (block sum vs warp sums)."""
+    n = nfb()
+    torch.manual_seed(7)
+    an, conv = n.flows.ActNorm(dims), n.flows.InvertibleConv1x1(dims[0])
+    cpl = n.flows.AffineCoupling(dims, masking=masking, odd=odd)
+    for m_, sd_ in ((an, 1), (conv, 2), (cpl, 3)):
+        perturb_(m_, sd_)
+    an.initialized = True
+    comp = n.flows.Compose([an, conv, cpl]).to(DEV).eval()
+    x = torch.randn((B, ) + dims, device=DEV)
+    l0 = torch.randn(B, device=DEV)
+    comp.fuse_steps = 2
+    comp(x, l0.clone())  # first call packs the conditioner weights / builds W (one-time launches)
+    n0 = n._lib.launch_count()
+    z1, l1 = comp(x, l0.clone())
+    assert n._lib.launch_count() - n0 == 1  # ONE kernel for the whole step
+    comp.fuse_steps = 0
+    z2, l2 = comp(x, l0.clone())
+    assert torch.equal(z1, z2)
+    close(l1, l2, rtol=1e-6, atol=1e-4, what='ldj')
