@@ -452,22 +452,29 @@ static int dispatch_convnet(const float* zsrc, float* out, const float* pk, cons
 // fused MLP (1-D couplings): one thread per sample, the 32 hidden activations in registers, weights in shared memory
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE>  // NFB_SPLIT_1D gathers z1 from z (row stride g.D); MODE < 0: x is (B, Cin)
-__global__ void __launch_bounds__(128) mlp_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
+__global__ void __launch_bounds__(256) mlp_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
                                                        const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
                                                        int B) {
-    extern __shared__ __align__(16) float sw[];  // the whole packed network
+    extern __shared__ __align__(16) float sw[];  // the whole packed network, then one 32x33 transpose tile per warp
     const PackLayout L = pack_layout(Cin, Cout, 1);
     for (int i = threadIdx.x * 4; i < L.total; i += blockDim.x * 4) st4(sw + i, ldg4(pk + i));
     __syncthreads();
     const int CoutPad = (Cout + 31) & ~31;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = sw + ((L.total + 3) & ~3) + warp * (32 * 33);
+    // warp-uniform loop (every lane of a warp iterates the same number of times: the tile transpose is collective)
+    for (int b0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32; b0 < B; b0 += gridDim.x * blockDim.x) {
+        const int b = b0 + lane;
+        const bool live = b < B;
         float x[kF], a[kF], y[kF];
 #pragma unroll
         for (int o = 0; o < kF; ++o) x[o] = sw[L.b0 + o];
         for (int ci = 0; ci < Cin; ++ci) {
-            float v;
-            if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(b) * Cin + ci);
-            else v = __ldg(zsrc + static_cast<size_t>(b) * g.D + 2 * ci + (g.odd ? 0 : 1));  // z1 of squeeze1d
+            float v = 0.f;
+            if (live) {
+                if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(b) * Cin + ci);
+                else v = __ldg(zsrc + static_cast<size_t>(b) * g.D + 2 * ci + (g.odd ? 0 : 1));  // z1 of squeeze1d
+            }
             const float* wr = sw + L.w0 + ci * kF;
 #pragma unroll
             for (int o = 0; o < kF; ++o) x[o] = fmaf(wr[o], v, x[o]);
@@ -507,9 +514,17 @@ __global__ void __launch_bounds__(128) mlp_fused_kernel(const float* __restrict_
 #pragma unroll
                 for (int o = 0; o < kF; ++o) y[o] = fmaf(wr[o], a[ci], y[o]);
             }
+            // lane owns a sample; transpose the 32 samples x 32 outputs block through shared memory so that every
+            // warp store is one contiguous 128-byte row of the (B, Cout) output
+            __syncwarp();
 #pragma unroll
-            for (int o = 0; o < kF; ++o)
-                if (c * kF + o < Cout) out[static_cast<size_t>(b) * Cout + c * kF + o] = y[o];
+            for (int o = 0; o < kF; ++o) tile[lane * 33 + o] = y[o];
+            __syncwarp();
+            const int oc = c * kF + lane;
+            if (oc < Cout) {
+                const int rows = (B - b0) < 32 ? (B - b0) : 32;
+                for (int r = 0; r < rows; ++r) out[static_cast<size_t>(b0 + r) * Cout + oc] = tile[r * 33 + lane];
+            }
         }
     }
 }
@@ -619,16 +634,17 @@ extern "C" int nfb_mlp_fwd(const float* src, float* params_out, const float* pac
     if (!src || !params_out || !packed) return NFB_ERR_NULL;
     if (in_ch <= 0 || out_ch <= 0 || B <= 0) return NFB_ERR_SHAPE;
     const PackLayout L = pack_layout(in_ch, out_ch, 1);
-    const size_t smem = static_cast<size_t>(L.total) * sizeof(float);
-    if (smem > 200 * 1024) return NFB_ERR_UNSUPPORTED;
+    const int threads = 256;
+    const size_t smem = (static_cast<size_t>((L.total + 3) & ~3) + (threads / 32) * 32 * 33) * sizeof(float);
+    if (smem > 220 * 1024) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     SplitGeom g{};
-    int blocks = (B + 127) / 128;
+    int blocks = (B + threads - 1) / threads;
     if (blocks > kSMs * 4) blocks = kSMs * 4;
     if (mode < 0) {
         auto kern = mlp_fused_kernel<-1>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<blocks, 128, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
+        kern<<<blocks, threads, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
         return launch_status();
     }
     const int rc = make_geom(g, B, C, 1, 1, NFB_SPLIT_1D, odd);
@@ -636,6 +652,6 @@ extern "C" int nfb_mlp_fwd(const float* src, float* params_out, const float* pac
     if (mode != NFB_SPLIT_1D || g.c0 != in_ch) return NFB_ERR_SHAPE;
     auto kern = mlp_fused_kernel<NFB_SPLIT_1D>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<blocks, 128, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
+    kern<<<blocks, threads, smem, st>>>(src, params_out, packed, g, in_ch, out_ch, B);
     return launch_status();
 }
