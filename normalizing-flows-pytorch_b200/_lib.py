@@ -107,3 +107,8 @@ def ptr(t):
 
 def launch_count():
     return int(lib().nfb_launch_count())
+
+
+def empty_batch(t):
+    """B == 0: nothing to launch (the reference returns empty tensors); the C ABI itself rejects B <= 0."""
+    return t.numel() == 0

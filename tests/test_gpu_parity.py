@@ -491,3 +491,68 @@ def test_fused_glow_step_matches_separate_layers(dims, masking, odd, B):
     z2, l2 = comp(x, l0.clone())
     assert torch.equal(z1, z2)
     close(l1, l2, rtol=1e-6, atol=1e-4, what='ldj')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# edge cases: ragged / odd shapes take the scalar kernels, B = 1, non-power-of-two widths, big channel counts
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dims,masking', [((2, 6, 6), 'checkerboard'), ((4, 2, 2), 'channelwise'), ((3, 24, 40), 'checkerboard'),
+                                          ((6, 10, 12), 'channelwise'), ((10, ), 'checkerboard'), ((1, 4, 4), 'checkerboard'),
+                                          ((5, 8, 8), 'checkerboard')])
+@pytest.mark.parametrize('B', [1, 5])
+def test_affine_bijection_odd_shapes_vs_oracle(dims, masking, B):
+    """The bijection kernel alone (conditioner output given) on shapes that miss the vector paths."""
+    import nfb200._lib as L
+    mode = L.SPLIT_1D if len(dims) == 1 else (L.SPLIT_CHECKER if masking == 'checkerboard' else L.SPLIT_CHANNEL)
+    C, H, W = (dims[0], 1, 1) if len(dims) == 1 else dims
+    g = torch.Generator().manual_seed(B)
+    z = torch.randn((B, ) + dims, generator=g)
+    params = torch.randn((B, ) + dims, generator=g)  # (t | s_raw): D entries per sample
+    a, b = torch.tensor([0.4]), torch.tensor([0.02])
+    ldj0 = torch.randn(B, generator=g)
+    for odd in (False, True):
+        split, merge = O.split_fn(len(dims), masking, odd)
+        z0, z1 = split(z)
+        p = params.reshape((B, 2 * z0.shape[1]) + tuple(z0.shape[2:]))
+        for inverse in (False, True):
+            o0, lo = O.affine_transform(z0, p, ldj0, a, b, inverse)
+            ref = merge(o0, z1)
+            zg, out, lg = z.to(DEV), torch.empty_like(z, device=DEV), ldj0.to(DEV).clone()
+            fn = L.lib().nfb_affine_coupling_inv if inverse else L.lib().nfb_affine_coupling_fwd
+            L.check(fn(zg.data_ptr(), out.data_ptr(), p.to(DEV).contiguous().data_ptr(), lg.data_ptr(), lg.data_ptr(),
+                       a.to(DEV).data_ptr(), b.to(DEV).data_ptr(), B, C, H, W, mode, int(odd), L.stream()))
+            close(out, ref, what='z %s odd=%s inv=%s' % (dims, odd, inverse))
+            close(lg, lo, rtol=1e-5, atol=1e-5, what='ldj')
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 2, 2), (2, 5, 6, 10), (1, 7, 24, 40), (3, 2, 14, 6)])
+def test_simple_layers_odd_shapes_vs_oracle(shape):
+    F = nfb().flows
+    torch.manual_seed(shape[1])
+    B, C = shape[:2]
+    x = torch.rand(shape)
+    l0 = torch.randn(B)
+    z, l = F.Logit(0.01)(x.to(DEV), l0.to(DEV))
+    zo, lo = O.logit_fwd(x, l0, 0.01)
+    close(z, zo)
+    close(l, lo, rtol=1e-5, atol=1e-4)
+    an = F.ActNorm(shape[1:])
+    perturb_(an, 3)
+    an.initialized = True
+    zo, lo = O.actnorm_fwd(x, l0, an.log_scale.data, an.bias.data)
+    z, l = an.to(DEV)(x.to(DEV), l0.to(DEV).clone())
+    close(z, zo)
+    close(l, lo, rtol=1e-5, atol=1e-4)
+    conv = F.InvertibleConv1x1(C)
+    perturb_(conv, 4)
+    sd = {k: v.clone() for k, v in conv.state_dict().items()}
+    zo, lo = O.invconv_fwd(x, l0, sd['P'], sd['L'], sd['U'], sd['log_s'], sd['sign_s'])
+    conv.to(DEV)
+    z, l = conv(x.to(DEV), l0.to(DEV).clone())
+    close(z, zo)
+    close(l, lo, rtol=1e-5, atol=1e-4)
+    y, l2 = conv.backward(z, l)
+    close(y, x, rtol=1e-4, atol=1e-4)
+    close(l2, l0, rtol=1e-5, atol=1e-4)
+    rows, total = nfb().gauss_nll(z, l)
+    close(rows, O.nll_rows(zo, lo).float(), rtol=1e-5, atol=1e-3)
