@@ -518,9 +518,11 @@ def test_affine_bijection_odd_shapes_vs_oracle(dims, masking, B):
             o0, lo = O.affine_transform(z0, p, ldj0, a, b, inverse)
             ref = merge(o0, z1)
             zg, out, lg = z.to(DEV), torch.empty_like(z, device=DEV), ldj0.to(DEV).clone()
+            pg, ag, bg = p.to(DEV).contiguous(), a.to(DEV), b.to(DEV)  # keep alive until the kernel has run
             fn = L.lib().nfb_affine_coupling_inv if inverse else L.lib().nfb_affine_coupling_fwd
-            L.check(fn(zg.data_ptr(), out.data_ptr(), p.to(DEV).contiguous().data_ptr(), lg.data_ptr(), lg.data_ptr(),
-                       a.to(DEV).data_ptr(), b.to(DEV).data_ptr(), B, C, H, W, mode, int(odd), L.stream()))
+            L.check(fn(zg.data_ptr(), out.data_ptr(), pg.data_ptr(), lg.data_ptr(), lg.data_ptr(), ag.data_ptr(),
+                       bg.data_ptr(), B, C, H, W, mode, int(odd), L.stream()))
+            torch.cuda.synchronize()
             close(out, ref, what='z %s odd=%s inv=%s' % (dims, odd, inverse))
             close(lg, lo, rtol=1e-5, atol=1e-5, what='ldj')
 
