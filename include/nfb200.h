@@ -198,6 +198,15 @@ int nfb_glow_step_fwd(const float* z_in, float* z_out, const float* ldj_in, floa
                       const float* s_log_scale, const float* s_bias, int B, int C, int H, int W, int mode, int odd,
                       nfb_stream_t stream);
 
+/* Flow++ conditioner (coupling.py:160-167: Conv2d(in,32,3) -> GatedConv2d -> LayerNorm -> GatedAttn(4 heads) ->
+ * LayerNorm -> Conv2d(32,out,3); modules.py:519-578) as ONE kernel.  `tensors`: HOST array of 15 device pointers:
+ * net.0 weight packed by nfb_pack_conv3x3, net.0.bias, net.1.op weight packed, net.1.op.bias, net.2.weight, net.2.bias,
+ * net.3.pos_emb, net.3.conv1.weight (96,32), net.3.conv1.bias, net.3.conv2.weight (64,32), net.3.conv2.bias,
+ * net.4.weight, net.4.bias, net.5 weight packed, net.5.bias.  src / mode / spatial sizes as for nfb_convnet_fwd. */
+int nfb_pack_conv3x3(const float* w, float* out, int O, int I, nfb_stream_t stream); /* (O,I,3,3) -> [O/32][I][9][32] */
+int nfb_flowpp_cond_fwd(const float* const* tensors, const float* src, float* params_out, int B, int C, int H, int W,
+                        int mode, int odd, int in_ch, int out_ch, nfb_stream_t stream);
+
 /* params_out (B, out_ch) = MLP(z1).  mode = NFB_SPLIT_1D: src = z (B, C), z1 gathered (squeeze.py:64-72);
  * mode < 0: src = (B, in_ch). */
 int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd, int in_ch,

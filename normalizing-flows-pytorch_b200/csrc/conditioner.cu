@@ -73,58 +73,6 @@ __global__ void pack_bn_kernel(const float* __restrict__ w, const float* __restr
 // ---------------------------------------------------------------------------------------------------------
 // fused ConvNet
 // ---------------------------------------------------------------------------------------------------------
-// OCT output channels x 4 pixels per thread, one 3x3 layer over CI input channels held in shared memory.
-template <int OCT>
-__device__ __forceinline__ void load_w(float (&wv)[OCT], const float* __restrict__ p) {
-    if (OCT == 8) {
-        const float4 a = ld4(p), b = ld4(p + 4);
-        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
-        wv[4 % OCT] = b.x; wv[5 % OCT] = b.y; wv[6 % OCT] = b.z; wv[7 % OCT] = b.w;
-    } else if (OCT == 4) {
-        const float4 a = ld4(p);
-        wv[0] = a.x; wv[1] = a.y; wv[2 % OCT] = a.z; wv[3 % OCT] = a.w;
-    } else if (OCT == 2) {
-        const float2 a = *reinterpret_cast<const float2*>(p);
-        wv[0] = a.x; wv[1 % OCT] = a.y;
-    } else {
-#pragma unroll
-        for (int o = 0; o < OCT; ++o) wv[o] = p[o];
-    }
-}
-
-template <int H, int W, int OCT>
-__device__ __forceinline__ void conv3x3_acc(float (&acc)[OCT][4], const float* __restrict__ a_base /* bufA + sample base */,
-                                            int chs, const float* __restrict__ wst /* [ci][9][32] */, int CI, int og,
-                                            int y, int x0) {
-    const bool left_edge = (x0 == 0), right_edge = (x0 + 4 == W);
-#pragma unroll 2
-    for (int ci = 0; ci < CI; ++ci) {
-        const float* a = a_base + ci * chs + y * W + x0;  // padded row index y+ky, ky = 0..2
-        const float* wrow = wst + ci * 9 * kF + og * OCT;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const float4 c = ld4(a + ky * W);
-            float l = 0.f, r = 0.f;
-            if (W > 4) {
-                l = __shfl_up_sync(0xffffffffu, c.w, 1);
-                r = __shfl_down_sync(0xffffffffu, c.x, 1);
-                if (left_edge) l = 0.f;
-                if (right_edge) r = 0.f;
-            }
-            const float av[6] = {l, c.x, c.y, c.z, c.w, r};
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                float wv[OCT];
-                load_w<OCT>(wv, wrow + (ky * 3 + kx) * kF);
-#pragma unroll
-                for (int o = 0; o < OCT; ++o)
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) acc[o][p] = fmaf(wv[o], av[p + kx], acc[o][p]);
-            }
-        }
-    }
-}
-
 // Arguments of the fused flow step (ActNorm -> InvertibleConv1x1 -> AffineCoupling in one launch).
 struct StepArgs {
     const float* z_in;      // (B, C, Hf, Wf) input of the step

@@ -4,6 +4,8 @@ and the per-sample log-det fused into one libnfb200 kernel each.
 Only the conditioner input z1 is materialised (one gather); z0, (t, s), the merged output and the log-det never
 exist as separate tensors.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -128,10 +130,52 @@ class MixLogAttnCoupling(AbstractCoupling):
         self._scratch = None
         self._flag = None
 
+    # -- fused conditioner kernel (image case): packed 3x3 weights cached until a parameter changes ------------------
+    def _fpp_tensors(self):
+        n = self.net
+        if getattr(self, '_fpp_ts', None) is None:
+            self._fpp_ts = [n[0].weight, n[0].bias, n[1].op.weight, n[1].op.bias, n[2].weight, n[2].bias, n[3].pos_emb,
+                            n[3].conv1.weight, n[3].conv1.bias, n[3].conv2.weight, n[3].conv2.bias, n[4].weight, n[4].bias,
+                            n[5].weight, n[5].bias]
+        ts = self._fpp_ts
+        key = tuple([t._version for t in ts])
+        if key != getattr(self, '_fpp_key', None):
+            packed = {}
+            for i in (0, 2, 13):
+                w = L.dev(ts[i].data, 'conv weight')
+                O, I = w.size(0), w.size(1)
+                buf = torch.empty(((O + 31) // 32) * 32 * I * 9, device=w.device, dtype=torch.float32)
+                L.check(L.lib().nfb_pack_conv3x3(L.ptr(w), L.ptr(buf), O, I, L.stream()))
+                packed[i] = buf
+            self._fpp_packed = packed
+            ptrs = [L.ptr(packed[i]) if i in packed else L.ptr(L.dev(t.data, 'conditioner parameter'))
+                    for i, t in enumerate(ts)]
+            self._fpp_arr = (ctypes.c_void_p * 15)(*ptrs)
+            self._fpp_key = key
+        return self._fpp_arr
+
+    def _apply(self, fn, *a, **k):
+        self._fpp_ts = self._fpp_key = None
+        return super()._apply(fn, *a, **k)
+
     def _params(self, z):
+        if z.dim() == 4 and not self.net.training and self.fused_conditioner:
+            B, C, H, W = z.shape
+            h, w = (H // 2, W // 2) if self.mode == L.SPLIT_CHECKER else (H, W)
+            n_out = sum(self.sections)
+            out = torch.empty((B, n_out, h, w), device=z.device, dtype=torch.float32)
+            in_chs = C * 2 if self.mode == L.SPLIT_CHECKER else C // 2
+            rc = L.lib().nfb_flowpp_cond_fwd(self._fpp_tensors(), L.ptr(z), L.ptr(out), B, C, H, W, self.mode,
+                                             int(self.odd), in_chs, n_out, L.stream())
+            if rc != L.ERR_UNSUPPORTED:
+                L.check(rc)
+                return out
+        # library path (torch ops on the device): 1-D inputs and spatial sizes the kernel does not cover
         _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
         with torch.no_grad():
             return L.dev(self.net(z1), 'conditioner output')
+
+    fused_conditioner = True
 
     def _run(self, z, ldj, inverse):
         B, C, H, W = self._geom(z)

@@ -558,3 +558,42 @@ def test_simple_layers_odd_shapes_vs_oracle(shape):
     close(l2, l0, rtol=1e-5, atol=1e-4)
     rows, total = nfb().gauss_nll(z, l)
     close(rows, O.nll_rows(zo, lo).float(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize('dims,masking,K', [((3, 32, 32), 'checkerboard', 8), ((12, 16, 16), 'channelwise', 8),
+                                            ((12, 16, 16), 'checkerboard', 4), ((48, 8, 8), 'channelwise', 8),
+                                            ((48, 8, 8), 'checkerboard', 8)])
+@pytest.mark.parametrize('B', [3, 32])
+def test_flowpp_conditioner_kernel_vs_oracle(dims, masking, K, B):
+    """One-kernel Flow++ conditioner (conv -> gated conv -> LN -> gated attention -> LN -> conv) vs the CPU oracle and vs
+    the torch-ops path on the device."""
+    F = nfb().flows
+    from nfb200.flows.squeeze import coupling_split
+    torch.manual_seed(K + dims[0])
+    cpl = F.MixLogAttnCoupling(dims, masking=masking, odd=False, n_mixtures=K)
+    with torch.no_grad():
+        for n_, p in cpl.named_parameters():
+            if 'pos_emb' in n_:
+                p.add_(0.1 * torch.randn(p.shape))
+            elif n_.endswith(('2.weight', '4.weight')):  # LayerNorm gains
+                p.add_(0.2 * torch.randn(p.shape))
+            elif n_.endswith(('2.bias', '4.bias')):
+                p.add_(0.1 * torch.randn(p.shape))
+    cpl.eval()
+    sd = {k: v.clone() for k, v in cpl.state_dict().items()}
+    z = torch.randn((B, ) + dims)
+    split, _ = O.split_fn(3, masking, False)
+    with torch.no_grad():
+        ref = O.flowpp_conditioner(sd, 'net.', split(z)[1])
+        ref64 = O.flowpp_conditioner(O.to_dtype(sd, torch.float64), 'net.', split(z)[1].double())
+    cpl.to(DEV)
+    fused = cpl._params(z.to(DEV))
+    cpl.fused_conditioner = False
+    lib = cpl._params(z.to(DEV))
+    scale = max(1.0, float(ref.abs().max()))
+    e_f = float((fused.cpu().double() - ref64).abs().max())
+    e_r = float((ref.double() - ref64).abs().max())
+    e_l = float((lib.cpu().double() - ref64).abs().max())
+    print('flow++ conditioner err vs fp64: kernel %.3e | torch-gpu %.3e | cpu fp32 %.3e | scale %.2f' % (e_f, e_l, e_r, scale))
+    close(fused, ref, rtol=2e-5, atol=5e-6 * scale, what='fused flow++ conditioner vs oracle')
+    assert e_f <= 6.0 * max(e_r, e_l) + 1e-6 * scale
