@@ -336,48 +336,89 @@ def run_nfb200(args, rank, world, local_rank):
         launches_per_step = nfb200._lib.launch_count() - n0
         torch.cuda.synchronize()
 
-        # ---- CUDA graph of one step ---------------------------------------------------------------
-        x_static = dev_ring[0].clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
+        # ---- CUDA graphs of one step: `streams` batches in flight, one graph + static buffers per stream ----------
+        n_str = max(1, args.streams)
+        lanes = []
+        for k in range(n_str):
+            st = torch.cuda.Stream()
+            x_static = dev_ring[0].clone()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                for _ in range(2):
+                    z, ldj = net(x_static)
+                    rows, total = nfb200.gauss_nll(z, ldj)
+            st.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=st):
                 z, ldj = net(x_static)
                 rows, total = nfb200.gauss_nll(z, ldj)
-        torch.cuda.current_stream().wait_stream(side)
+            lanes.append(dict(stream=st, x=x_static, graph=graph, rows=rows, total=total,
+                              red=torch.zeros(2, device=dev, dtype=torch.float64),
+                              host_total=torch.zeros(2, dtype=torch.float64).pin_memory(),
+                              host_rows=torch.zeros(batch, dtype=torch.float32).pin_memory()))
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            z, ldj = net(x_static)
-            rows, total = nfb200.gauss_nll(z, ldj)
-        tot_red = torch.zeros(2, device=dev, dtype=torch.float64)
+        x_static, graph, rows, total = lanes[0]['x'], lanes[0]['graph'], lanes[0]['rows'], lanes[0]['total']
 
-        def step(i):
-            x_static.copy_(dev_ring[i % ring_n], non_blocking=True)
-            graph.replay()
+        def step(i, lanes_used, src_ring, read_back):
+            ln = lanes[i % lanes_used]
+            with torch.cuda.stream(ln['stream']):
+                ln['x'].copy_(src_ring[i % ring_n], non_blocking=True)  # device ring (value) or pinned host ring (e2e)
+                ln['graph'].replay()
+                res = ln['total']
+                if world > 1:
+                    ln['red'].copy_(ln['total'])
+                    dist.all_reduce(ln['red'])
+                    res = ln['red']
+                if read_back:
+                    ln['host_total'].copy_(res, non_blocking=True)
+                    ln['host_rows'].copy_(ln['rows'], non_blocking=True)  # per-sample NLL (= -log p(y), main.py:121-124)
+            return ln
+
+        def timed(lanes_used, src_ring, read_back):
+            """K steps, `lanes_used` batches in flight; device time from CUDA events on the launching stream, which forks
+            to / joins the lane streams."""
+            cur = torch.cuda.current_stream()
+            for i in range(args.warmup):
+                step(i, lanes_used, src_ring, read_back)
+            for ln in lanes:
+                cur.wait_stream(ln['stream'])
+            torch.cuda.synchronize()
             if world > 1:
-                tot_red.copy_(total)
-                dist.all_reduce(tot_red)
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            for ln in lanes[:lanes_used]:
+                ln['stream'].wait_event(e0)
+            pending = []
+            for i in range(args.steps):
+                ln = step(args.warmup + i, lanes_used, src_ring, read_back)
+                if read_back:  # the caller consumes every result: wait for the step that used this lane before reusing it
+                    pending.append(ln)
+                    if len(pending) >= lanes_used:
+                        p = pending.pop(0)
+                        p['stream'].synchronize()
+                        _ = p['host_total'][0].item()
+            for p in pending:
+                p['stream'].synchronize()
+                _ = p['host_total'][0].item()
+            for ln in lanes[:lanes_used]:
+                cur.wait_stream(ln['stream'])
+            e1.record(cur)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
 
-        for i in range(args.warmup):
-            step(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        ms_single = timed(1, dev_ring, False)  # one batch in flight (also the latency of a step)
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         t_wall = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            step(args.warmup + i)
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        ms = timed(n_str, dev_ring, False)
         wall = time.perf_counter() - t_wall
-        ms = e0.elapsed_time(e1)
         if ms * 1e-3 < 1.0 and rank == 0:
             # make sure the clock sampler saw the load: keep the GPU busy a little longer (untimed)
             t_end = time.perf_counter() + 1.0
@@ -385,51 +426,17 @@ def run_nfb200(args, rank, world, local_rank):
                 graph.replay()  # local work only: no collective outside the steps every rank executes
             torch.cuda.synchronize()
         clocks = sampler.stop() if rank == 0 else None
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         value = batch * world * args.steps / (ms * 1e-3)
+        value_single = batch * world * args.steps / (ms_single * 1e-3)
 
-        # ---- end-to-end leg: public API, pinned host inputs, result read back every step ------------------
-        host_total = torch.zeros(2, dtype=torch.float64).pin_memory()
-        host_rows = torch.zeros(batch, dtype=torch.float32).pin_memory()
-
-        def e2e_step(i):
-            x_static.copy_(host_ring[i % ring_n], non_blocking=True)  # H2D from pinned memory
-            graph.replay()  # net.forward + gauss_nll as captured from the public API
-            if world > 1:
-                tot_red.copy_(total)
-                dist.all_reduce(tot_red)
-                host_total.copy_(tot_red, non_blocking=True)
-            else:
-                host_total.copy_(total, non_blocking=True)
-            host_rows.copy_(rows, non_blocking=True)  # per-sample NLL (= -log p(y), main.py:121-124)
-            torch.cuda.current_stream().synchronize()  # the caller reads the result every step
-            return host_total[0].item()
-
-        for i in range(args.warmup):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for i in range(args.steps):
-            e2e_step(args.warmup + i)
-        s1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        # ---- end-to-end leg: public API (captured), pinned host inputs, result read back every step ----------------
+        e2e_ms = timed(n_str, host_ring, True)
         e2e_value = batch * world * args.steps / (e2e_ms * 1e-3)
 
         # ---- bits/dim of the (global) batch ring[0] ------------------------------------------------------
         x_static.copy_(dev_ring[0])
         graph.replay()
+        torch.cuda.synchronize()
         bpd_local = nfb200.bits_per_dim_from_total(total, D)
         bpd_global = parallel.global_bits_per_dim(total, D)
         torch.cuda.synchronize()
@@ -472,7 +479,11 @@ def run_nfb200(args, rank, world, local_rank):
                    'l2': 'inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)' %
                          (ring_n, ring_n * bytes_per_batch / 1e6),
                    'parallelism': 'sample-sharded replicas x%d, all-reduce of (sum NLL, count) only' % world,
-                   'timing': 'CUDA events around K graph replays, max over ranks', 'wall_s': wall},
+                   'batches_in_flight': n_str,
+                   'timing': 'CUDA events around K graph replays (%d batches in flight on %d streams), max over ranks' % (n_str, n_str),
+                   'wall_s': wall},
+        'single_stream': {'value': value_single, 'ms_per_step': ms_single / args.steps,
+                          'note': 'one batch in flight: ms_per_step is then the latency of a step'},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'h2d_bytes_per_step': bytes_per_batch, 'd2h_bytes_per_step': 16 + 4 * batch},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
@@ -509,6 +520,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='nfb200', choices=['nfb200', 'reference'])
     ap.add_argument('--workload', default='glow32', choices=sorted(WORKLOADS))
+    ap.add_argument('--streams', type=int, default=3, help='batches in flight (one CUDA graph + stream each)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'nfb200' else args.warmup
 

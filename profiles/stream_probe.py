@@ -41,9 +41,41 @@ lg = nfb200.flows.Logit(0.01)
 zz = torch.rand((B, ) + dims, device='cuda')
 cases.append(('logit 3x32x32', lambda: lg(zz, ldj), 8 * D + 8))
 cases.append(('copy_ (torch) same bytes as 8D', lambda: out.copy_(z), 8 * D))
-for name, fn, bytes_per_sample in cases:
+# mixture-CDF (Flow++) and RQ-spline couplings at streaming size: params are (2+3K) / (3K-1) values per transformed element
+K = 8
+Bm = 4096
+zm = torch.randn((Bm, ) + dims, device='cuda')
+outm = torch.empty_like(zm)
+ldjm = torch.zeros(Bm, device='cuda')
+pm = torch.randn(Bm, (2 + 3 * K) * (D // 2), device='cuda') * 0.5
+cases.append(('mixlog fwd K=8 checker 3x32x32 (B=4096)', lambda: L.check(L.lib().nfb_mixlog_coupling_fwd(
+    zm.data_ptr(), outm.data_ptr(), pm.data_ptr(), ldjm.data_ptr(), ldjm.data_ptr(), a.data_ptr(), b.data_ptr(), Bm, 3, 32, 32,
+    L.SPLIT_CHECKER, 0, K, st)), (12 + 6 * K) * D + 8, Bm))
+pr = torch.randn(Bm, (3 * K - 1) * (D // 2), device='cuda')
+cases.append(('rqs fwd K=8 checker 3x32x32 (B=4096)', lambda: L.check(L.lib().nfb_rqs_coupling_fwd(
+    zm.data_ptr(), outm.data_ptr(), pr.data_ptr(), ldjm.data_ptr(), ldjm.data_ptr(), Bm, 3, 32, 32, L.SPLIT_CHECKER, 0, K, 3.0,
+    st)), (8 + 2 * (3 * K - 1)) * D + 8, Bm))
+z1d = torch.randn(1 << 20, 64, device='cuda')
+o1d = torch.empty_like(z1d)
+l1d = torch.zeros(1 << 20, device='cuda')
+p1d = torch.randn(1 << 20, 23 * 32, device='cuda')
+cases.append(('rqs fwd K=8 1-D D=64 (B=2^20)', lambda: L.check(L.lib().nfb_rqs_coupling_fwd(
+    z1d.data_ptr(), o1d.data_ptr(), p1d.data_ptr(), l1d.data_ptr(), l1d.data_ptr(), 1 << 20, 64, 1, 1, L.SPLIT_1D, 0, K, 3.0,
+    st)), (8 + 2 * 23) * 64 + 8, 1 << 20))
+pa1 = torch.randn(1 << 20, 64, device='cuda')
+cases.append(('affine 1-D D=64 (B=2^20)', lambda: L.check(L.lib().nfb_affine_coupling_fwd(
+    z1d.data_ptr(), o1d.data_ptr(), pa1.data_ptr(), l1d.data_ptr(), l1d.data_ptr(), a.data_ptr(), b.data_ptr(), 1 << 20, 64, 1, 1,
+    L.SPLIT_1D, 0, st)), 12 * 64 + 8, 1 << 20))
+sq = torch.empty(B, 12, 16, 16, device='cuda')
+cases.append(('squeeze2d 3x32x32', lambda: L.check(L.lib().nfb_squeeze2d(z.data_ptr(), sq.data_ptr(), B, 3, 32, 32, 0, st)), 8 * D, B))
+nr = torch.empty(B, device='cuda')
+tot = torch.empty(2, device='cuda', dtype=torch.float64)
+cases.append(('gauss_nll 3x32x32', lambda: L.check(L.lib().nfb_gauss_nll(z.data_ptr(), ldj.data_ptr(), nr.data_ptr(), tot.data_ptr(), B, D, st)), 4 * D + 8, B))
+for case in cases:
+    name, fn, bytes_per_sample = case[:3]
+    nb = case[3] if len(case) > 3 else B
     for _ in range(3):
         fn()
     mean, med, best = bench.time_kernel_stream(fn, 15, flush)
-    gbs = bytes_per_sample * B / (med * 1e-3) / 1e9
+    gbs = bytes_per_sample * nb / (med * 1e-3) / 1e9
     print('%-42s %8.1f us  %7.1f GB/s  %.3f of measured HBM peak' % (name, med * 1e3, gbs, gbs / peaks['hbm_gbs']))
