@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256, 4) rows_warp_kernel(F f, const float* ldj
 
 template <class F>
 inline int launch_rows(const F& f, const float* ldj_in, float* ldj_out, int B, cudaStream_t st) {
-    if (f.items > 32 && f.items <= 4096 && static_cast<long long>(B) * 32 >= static_cast<long long>(kSMs) * 2048) {
+    if (f.items > 32 && f.items <= 4096 && B >= kSMs * 64) {  // several waves of warps from the batch alone
         const int rows_per_block = 8;
         long long grid = (static_cast<long long>(B) + rows_per_block - 1) / rows_per_block;
         if (grid > kSMs * 64) grid = kSMs * 64;

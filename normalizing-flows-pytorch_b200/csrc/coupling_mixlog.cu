@@ -75,6 +75,14 @@ __device__ __forceinline__ float mix_eval(const MixParams<KT>& p, float x, int K
     return logf(cs) + cmax;
 }
 
+// log-domain evaluation exactly as modules.py:76-97,190-194 -- out of line so the fast path keeps its registers
+template <int KT>
+__device__ __noinline__ float mix_fwd_logdomain(const float* __restrict__ prow, int n0, int j, int K, float x, float& logpdf) {
+    MixParams<KT> p;
+    load_mix<KT>(p, prow, n0, j, K);
+    return expf(mix_eval<KT, true>(p, x, K, logpdf));
+}
+
 // ---- forward -------------------------------------------------------------------------------------------
 template <int MODE, int KT>
 struct MixFwd {
@@ -98,14 +106,46 @@ struct MixFwd {
         const float x = zin[zbase + e];
         const float a = __fadd_rn(__fmul_rn(tanhf(__ldg(prow + j)), __ldg(pa)), __ldg(pb));  // coupling.py:178
         const float b = __ldg(prow + g.n0 + j);
-        MixParams<KT> p;
-        load_mix<KT>(p, prow, g.n0, j, K);
-        float ld1;
-        const float logcdf = mix_eval<KT, true>(p, x, K, ld1);
-        float y = expf(logcdf);                                        // modules.py:194
+        // Fast path, linear domain: with e_k = exp(-|u_k|) the logistic cdf is 1/(1+e_k) (u >= 0) or e_k/(1+e_k), and the
+        // pdf is exp(-s_k) e_k/(1+e_k)^2; the mixture is a softmax-weighted sum.  2 exp + 1 reciprocal per component
+        // instead of 4 exp + 1 log1p.  exp(logsumexp(.)) of modules.py:85,97,194 is the same quantity; the log-domain
+        // formulation below takes over when the density underflows (far tails), so extreme inputs behave like the
+        // reference.
+        float ld1, y;
+        {
+            const float* base = prow + 2 * static_cast<size_t>(g.n0) + j;
+            float lp[KT ? KT : NFB_MAX_MIXTURES], mu[KT ? KT : NFB_MAX_MIXTURES], sv[KT ? KT : NFB_MAX_MIXTURES];
+#pragma unroll
+            for (int k = 0; k < kk; ++k) {  // all loads first: 3K independent requests in flight
+                lp[k] = __ldg(base + static_cast<size_t>(k) * g.n0);
+                mu[k] = __ldg(base + static_cast<size_t>(kk + k) * g.n0);
+                sv[k] = __ldg(base + static_cast<size_t>(2 * kk + k) * g.n0);
+            }
+            float mx = lp[0];
+#pragma unroll
+            for (int k = 1; k < kk; ++k) mx = fmaxf(mx, lp[k]);
+            float wsum = 0.f, cdf = 0.f, pdf = 0.f;
+#pragma unroll
+            for (int k = 0; k < kk; ++k) {
+                const float w = expf(lp[k] - mx);
+                const float inv = expf(-sv[k]);
+                const float u = __fmul_rn(__fsub_rn(x, mu[k]), inv);
+                const float ek = expf(-fabsf(u));
+                const float r = __fdiv_rn(1.f, 1.f + ek);
+                const float c_lo = ek * r;                            // sigma(-|u|); r = sigma(|u|)
+                wsum += w;
+                cdf = fmaf(w, u >= 0.f ? r : c_lo, cdf);
+                pdf = fmaf(w * inv, r * c_lo, pdf);
+            }
+            const float rw = __fdiv_rn(1.f, wsum);
+            y = cdf * rw;
+            ld1 = logf(pdf * rw);
+            if (!(pdf * rw > 1.0e-30f)) y = mix_fwd_logdomain<KT>(prow, g.n0, j, K, x, ld1);  // far tails: reference formulation
+        }
         y = fminf(fmaxf(y, kLogitEps), 1.f - kLogitEps);               // Logit.forward, modules.py:147
-        const float lg = logf(__fdiv_rn(y, __fsub_rn(1.f, y)));
-        const float ld2 = -log_dsigmoid_f(lg);
+        const float l0 = logf(y), l1 = logf(__fsub_rn(1.f, y));        // logit = log y - log(1-y); log-det = -(log y + log(1-y))
+        const float lg = __fsub_rn(l0, l1);
+        const float ld2 = -__fadd_rn(l0, l1);
         zout[zbase + e] = __fadd_rn(__fmul_rn(lg, expf(a)), b);        // coupling.py:187
         if (!inplace) {
             const int e1 = half_offset<MODE>(g, j, 1);

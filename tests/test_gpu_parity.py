@@ -553,10 +553,10 @@ def test_simple_layers_odd_shapes_vs_oracle(shape):
     z, l = conv(x.to(DEV), l0.to(DEV).clone())
     close(z, zo)
     close(l, lo, rtol=1e-5, atol=1e-4)
-    y, l2 = conv.backward(z, l)
+    rows, total = nfb().gauss_nll(z, l)
+    y, l2 = conv.backward(z, l.clone())  # backward accumulates into the tensor it is given
     close(y, x, rtol=1e-4, atol=1e-4)
     close(l2, l0, rtol=1e-5, atol=1e-4)
-    rows, total = nfb().gauss_nll(z, l)
     close(rows, O.nll_rows(zo, lo).float(), rtol=1e-5, atol=1e-3)
 
 
