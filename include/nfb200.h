@@ -185,7 +185,7 @@ int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int o
 /* params_out (B, out_ch, h, w) = ConvNet(z1).  mode = NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL: `src` is the coupling's
  * z (B, C, H, W) and the conditioner input z1 = the pass-through half is gathered on the fly (coupling.py:33,105);
  * mode < 0: `src` is the (B, in_ch, H, W) conditioner input itself (C ignored).  Supported spatial sizes of the
- * conditioner input: 16x16, 8x8, 4x4 (else NFB_ERR_UNSUPPORTED). */
+ * conditioner input: 32x32 (one 2-CTA cluster per sample), 16x16, 8x8, 4x4 (else NFB_ERR_UNSUPPORTED). */
 int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
                     int odd, int in_ch, int out_ch, nfb_stream_t stream);
 /* One whole Glow flow step (glow.py:27-29) in ONE launch: ActNorm.forward (modules.py:246-250) ->

@@ -12,6 +12,8 @@
 // the coupling's split addressing (no materialised split).  Arithmetic is FP32 FFMA: bits/dim parity at 1e-5 with a
 // reference noise floor of 2e-7 rules out single-pass TF32/BF16 tensor-core math; an error-compensated
 // tcgen05 path is the next step.
+#include <cooperative_groups.h>
+
 #include "conditioner.cuh"
 
 namespace nfb {
@@ -359,6 +361,208 @@ static int launch_convnet(const float* zsrc, float* out, const float* pk, const 
     return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 32x32 conditioner inputs (first level of a 64x64 Glow): one sample = a CLUSTER of two CTAs.
+// Each CTA owns 16 image rows (512 pixels, 512 threads, same 8 channels x 4 pixels thread tile); its padded buffer has
+// one halo row above and below.  After every layer the boundary row is written straight into the peer CTA's halo row
+// through distributed shared memory (cluster.map_shared_rank) and a cluster barrier replaces the block barrier.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+    convnet_cluster32_kernel(const float* __restrict__ zsrc, float* __restrict__ out, const float* __restrict__ pk, SplitGeom g,
+                             int Cin, int Cout, int B) {
+    namespace cg = cooperative_groups;
+    constexpr int HL = 16, W = 32, NT = 512, OCT = 8, HF = 32;  // local rows, width, threads, tile, full height
+    constexpr int NPG = NT / (kF / OCT);                         // 128 pixel groups = 16 rows x 8
+    constexpr int CHS = (HL + 2) * W;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank());     // 0: rows 0..15, 1: rows 16..31
+    extern __shared__ __align__(16) float smem[];
+    float* bufA = smem;                                          // [32][HL+2][W]
+    float* wbuf = smem + kF * CHS;                               // [2][kWStage]
+    float* peerA = cluster.map_shared_rank(bufA, rank ^ 1);
+
+    const PackLayout L = pack_layout(Cin, Cout, 9);
+    const int CoutPad = (Cout + 31) & ~31;
+    const int t = threadIdx.x;
+    const int pg = t % NPG, og = t / NPG;
+    const int y = pg / (W / 4), x0 = 4 * (pg % (W / 4));
+    const int b = blockIdx.x >> 1;
+    const int gy = rank * HL + y;                                // row in the full image
+
+    int pf_cnt = 0, use_cnt = 0;
+    auto prefetch = [&](const float* src, int nfloats) {
+        float* dst = wbuf + (pf_cnt & 1) * kWStage;
+        for (int i = t * 4; i < nfloats; i += NT * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+        ++pf_cnt;
+    };
+    const int n_in = (Cin + kF - 1) / kF;
+    const int n_out = CoutPad / kF;
+    const int n_stage = n_in + 4 + n_out;
+    auto stage_src = [&](int i, int& n) -> const float* {
+        if (i < n_in) {
+            const int ci = (Cin - i * kF) < kF ? (Cin - i * kF) : kF;
+            n = ci * 9 * kF;
+            return pk + L.w0 + i * kF * 9 * kF;
+        }
+        i -= n_in;
+        if (i < 4) { n = kWStage; return pk + ((i & 1) ? L.w2[i >> 1] : L.w1[i >> 1]); }
+        i -= 4;
+        n = kF * kF;
+        return pk + L.wout + i * kF * kF;
+    };
+    int stage = 0;
+    auto prefetch_stage = [&](int i) {
+        if (i < n_stage) { int n; const float* src = stage_src(i, n); prefetch(src, n); }
+    };
+    // weights of the current stage landed + every activation write (own and the peer's halo row) is visible
+    auto acquire = [&]() -> const float* {
+        cp_async_wait_all();
+        cluster.sync();
+        const float* w = wbuf + (use_cnt & 1) * kWStage;
+        ++use_cnt;
+        return w;
+    };
+
+    prefetch_stage(0);
+    for (int i = t; i < kF * CHS; i += NT) bufA[i] = 0.f;
+    __syncthreads();
+
+    float xres[OCT][4], acc[OCT][4];
+#pragma unroll
+    for (int o = 0; o < OCT; ++o)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+
+    // ---- in conv: both the interior rows and the two halo rows come straight from global memory -------------------
+    for (int c = 0; c < n_in; ++c) {
+        const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
+        if (c > 0) __syncthreads();
+        for (int i = t; i < CI * (HL + 2) * W; i += NT) {
+            const int ci = i / ((HL + 2) * W);
+            const int rem = i - ci * ((HL + 2) * W);
+            const int pr = rem / W, xx = rem - pr * W;
+            const int yy = rank * HL + pr - 1;
+            float v = 0.f;
+            if (yy >= 0 && yy < HF) {
+                const int j = (c * kF + ci) * (HF * W) + yy * W + xx;
+                if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(b) * Cin * (HF * W) + j);
+                else v = __ldg(zsrc + static_cast<size_t>(b) * g.D + half_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, j, 1));
+            }
+            bufA[ci * CHS + rem] = v;
+        }
+        const float* w = acquire();
+        prefetch_stage(++stage);
+        conv3x3_acc<HL, W, OCT>(acc, bufA, CHS, w, CI, og, y, x0);
+    }
+#pragma unroll
+    for (int o = 0; o < OCT; ++o) {
+        const float bias = __ldg(pk + L.b0 + og * OCT + o);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) xres[o][p] = acc[o][p] + bias;
+    }
+
+    // relu(scale*v + shift) -> own interior row, and into the peer's halo row when this is a boundary row
+    auto store_act = [&](const float (&v)[OCT][4], const float* sc_sh) {
+        cluster.sync();  // both CTAs finished reading the previous activations (including each other's halo rows)
+        const bool to_peer = (rank == 0 && y == HL - 1) || (rank == 1 && y == 0);
+        const int peer_row = rank == 0 ? 0 : HL + 1;  // my last row is the peer's top halo; my first row its bottom halo
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) {
+            const int ch = og * OCT + o;
+            const float sc = sc_sh ? __ldg(sc_sh + ch) : 1.f, sh = sc_sh ? __ldg(sc_sh + kF + ch) : 0.f;
+            float4 q;
+            q.x = fmaxf(fmaf(v[o][0], sc, sh), 0.f);
+            q.y = fmaxf(fmaf(v[o][1], sc, sh), 0.f);
+            q.z = fmaxf(fmaf(v[o][2], sc, sh), 0.f);
+            q.w = fmaxf(fmaf(v[o][3], sc, sh), 0.f);
+            st4(bufA + ch * CHS + (y + 1) * W + x0, q);
+            if (to_peer) st4(peerA + ch * CHS + peer_row * W + x0, q);
+        }
+    };
+
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+        store_act(xres, pk + L.bnA[blk]);
+        const float* w = acquire();
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        conv3x3_acc<HL, W, OCT>(acc, bufA, CHS, w, kF, og, y, x0);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) {
+            const float bias = __ldg(pk + L.b1[blk] + og * OCT + o);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] += bias;
+        }
+        store_act(acc, nullptr);
+        w = acquire();
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        conv3x3_acc<HL, W, OCT>(acc, bufA, CHS, w, kF, og, y, x0);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) {
+            const float bias = __ldg(pk + L.b2[blk] + og * OCT + o);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) xres[o][p] += acc[o][p] + bias;
+        }
+    }
+
+    store_act(xres, pk + L.bnO);  // the 1x1 output conv needs no halo, but the barrier pairing stays uniform
+    for (int c = 0; c < n_out; ++c) {
+        const float* w = acquire();
+        prefetch_stage(++stage);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+        const float* a = bufA + (y + 1) * W + x0;
+#pragma unroll 4
+        for (int ci = 0; ci < kF; ++ci) {
+            const float4 v = ld4(a + ci * CHS);
+            float wv[OCT];
+            load_w<OCT>(wv, w + ci * kF + og * OCT);
+#pragma unroll
+            for (int o = 0; o < OCT; ++o) {
+                acc[o][0] = fmaf(wv[o], v.x, acc[o][0]);
+                acc[o][1] = fmaf(wv[o], v.y, acc[o][1]);
+                acc[o][2] = fmaf(wv[o], v.z, acc[o][2]);
+                acc[o][3] = fmaf(wv[o], v.w, acc[o][3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) {
+            const int oc = c * kF + og * OCT + o;
+            if (oc < Cout) {
+                const float bias = __ldg(pk + L.bout + oc);
+                st4(out + ((static_cast<size_t>(b) * Cout + oc) * HF + gy) * W + x0,
+                    make_float4(acc[o][0] + bias, acc[o][1] + bias, acc[o][2] + bias, acc[o][3] + bias));
+            }
+        }
+    }
+    cluster.sync();  // no CTA may exit while its peer can still write into its shared memory
+}
+
+template <int MODE>
+static int launch_cluster32(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
+                            cudaStream_t st) {
+    constexpr size_t smem = (static_cast<size_t>(kF) * 18 * 32 + 2 * kWStage) * sizeof(float);
+    auto kern = convnet_cluster32_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = true;
+    }
+    kern<<<2 * B, 512, smem, st>>>(zsrc, out, pk, g, Cin, Cout, B);
+    return launch_status();
+}
+
 int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // runtime variant selection (nfb_set_tuning); 0 = default
 
 template <int MODE>
@@ -393,6 +597,7 @@ static int dispatch_convnet(const float* zsrc, float* out, const float* pk, cons
         }
     }
 #undef NFB_CONV
+    if (h == 32 && w == 32) return launch_cluster32<MODE>(zsrc, out, pk, g, Cin, Cout, B, st);
     return NFB_ERR_UNSUPPORTED;
 }
 

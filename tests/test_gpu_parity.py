@@ -336,7 +336,8 @@ def test_errors_are_loud():
 # fused conditioner kernels (ConvNet / MLP) vs the CPU oracle and vs the on-device library path
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('cin,cout,hw,B', [(6, 12, 16, 5), (24, 48, 8, 7), (96, 192, 4, 9), (2, 4, 8, 3),
-                                           (40, 70, 16, 2), (6, 12, 16, 256)])
+                                           (40, 70, 16, 2), (6, 12, 16, 256), (6, 12, 32, 3), (40, 70, 32, 2),
+                                           (6, 12, 32, 64)])
 def test_convnet_fused_vs_oracle(cin, cout, hw, B):
     F = nfb().flows
     torch.manual_seed(cin)
@@ -377,7 +378,8 @@ def test_mlp_fused_vs_oracle(cin, cout, B):
 
 @pytest.mark.parametrize('dims,masking', [((3, 32, 32), 'checkerboard'), ((12, 16, 16), 'channelwise'),
                                           ((12, 16, 16), 'checkerboard'), ((48, 8, 8), 'channelwise'),
-                                          ((48, 8, 8), 'checkerboard'), ((64, ), 'checkerboard')])
+                                          ((48, 8, 8), 'checkerboard'), ((64, ), 'checkerboard'),
+                                          ((3, 64, 64), 'checkerboard'), ((12, 32, 32), 'channelwise')])
 @pytest.mark.parametrize('odd', [False, True])
 def test_conditioner_gathers_z1_in_kernel(dims, masking, odd):
     """forward_from_z (split addressing inside the kernel) == explicit split followed by the conditioner, bit for bit."""
