@@ -123,6 +123,11 @@ int nfb_bnflow_inv(const float* z_in, float* z_out, const float* ldj_in, float* 
 int nfb_bnflow_batch_stats(const float* z, float* mean_out, float* var_out, int B, int C, int HW, float eps,
                            nfb_stream_t stream);
 
+/* Per-channel raw moments in fp64 over (batch, pixels): moments_out[c] = sum x, moments_out[C + c] = sum x^2 (device
+ * double[2C]).  Additive across ranks: the sharded form of the statistics behind ActNorm's init (modules.py:238-244) and
+ * the train-mode BatchNorm (modules.py:285-287); see nfb200.parallel. */
+int nfb_channel_moments(const float* z, double* moments_out, int B, int C, int HW, nfb_stream_t stream);
+
 /* Logit.forward (modules.py:146-150): x = clamp(x, lo, hi); y = logit(x); ldj += sum(-(y - 2 softplus(y))). */
 int nfb_logit_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, float lo, float hi, int B,
                   int D, nfb_stream_t stream);

@@ -38,6 +38,7 @@ _SIGNATURES = {
     'nfb_bnflow_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'nfb_bnflow_inv': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'nfb_bnflow_batch_stats': [_P, _P, _P, _I, _I, _I, _F, _P],
+    'nfb_channel_moments': [_P, _P, _I, _I, _I, _P],
     'nfb_logit_fwd': [_P, _P, _P, _P, _F, _F, _I, _I, _P],
     'nfb_logit_inv': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_invconv1x1_weight': [_P, _P, _P, _P, _P, _P, _P, _I, _P],

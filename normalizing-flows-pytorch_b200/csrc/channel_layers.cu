@@ -138,6 +138,26 @@ __global__ void __launch_bounds__(512) chan_stats_kernel(const float* __restrict
     }
 }
 
+// per-channel raw moments in fp64: out[c] = sum x, out[C + c] = sum x^2 over (batch, pixels).  Additive across ranks:
+// all-reduce (SUM) the 2C doubles and the element count, then finalise (parallel.py) -> statistics identical to a
+// single-process pass over the global batch (SURVEY.md 8e exceptions: ActNorm init, BatchNorm train mode).
+__global__ void __launch_bounds__(512) chan_moments_kernel(const float* __restrict__ z, double* __restrict__ out, int B, int C,
+                                                          int HW) {
+    __shared__ double red[33];
+    const int c = blockIdx.x;
+    const long long n = static_cast<long long>(B) * HW;
+    double s = 0.0, q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long b = i / HW, p = i - b * HW;
+        const double v = static_cast<double>(__ldg(z + (b * C + c) * HW + p));
+        s += v;
+        q += v * v;
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) { out[c] = s; out[C + c] = q; }
+}
+
 // ---- Logit ------------------------------------------------------------------------------------------
 template <bool INV, bool VEC>
 struct LogitRow {
@@ -242,4 +262,11 @@ extern "C" int nfb_logit_fwd(const float* z_in, float* z_out, const float* ldj_i
 extern "C" int nfb_logit_inv(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, int B, int D,
                              nfb_stream_t stream) {
     return launch_logit<true>(z_in, z_out, ldj_in, ldj_out, 0.f, 1.f, B, D, stream);
+}
+
+extern "C" int nfb_channel_moments(const float* z, double* moments_out, int B, int C, int HW, nfb_stream_t stream) {
+    if (!z || !moments_out) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    chan_moments_kernel<<<C, 512, 0, as_stream(stream)>>>(z, moments_out, B, C, HW);
+    return launch_status();
 }

@@ -39,3 +39,56 @@ def sharded_bits_per_dim(model, x_local, group=None):
     """bits/dim of the GLOBAL batch given this rank's shard `x_local` (already on this rank's GPU)."""
     _, total = model.nll(x_local)
     return global_bits_per_dim(total, x_local[0].numel(), group)
+
+
+# ---- cross-sample statistics on a sharded batch (SURVEY.md 8e: the places where samples are NOT independent) ----------
+
+
+def channel_moments(z):
+    """device double[2C + 1] = (sum x per channel, sum x^2 per channel, element count per channel) of this rank's shard."""
+    from . import _lib as L
+    z = L.dev(z, 'z')
+    B, C = z.size(0), z.size(1)
+    HW = z[0, 0].numel() if z.dim() > 2 else 1
+    out = torch.empty(2 * C + 1, device=z.device, dtype=torch.float64)
+    L.check(L.lib().nfb_channel_moments(L.ptr(z), out.data_ptr(), B, C, HW, L.stream()))
+    out[2 * C] = float(B * HW)
+    return out
+
+
+def finalize_moments(m):
+    """(mean, biased variance, unbiased variance, n) per channel from (all-reduced) moments, in fp64."""
+    C = (m.numel() - 1) // 2
+    n = m[2 * C]
+    mean = m[:C] / n
+    ss = torch.clamp(m[C:2 * C] - n * mean * mean, min=0.0)
+    return mean, ss / n, ss / torch.clamp(n - 1, min=1.0), n
+
+
+def actnorm_init_sharded(layer, z_local, group=None):
+    """ActNorm's data-dependent init (modules.py:238-244) from the GLOBAL batch when every rank holds a shard: one
+    all-reduce of 2C+1 doubles; every rank ends up with identical log_scale / bias."""
+    m = channel_moments(z_local)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group)
+    mean, _, var_unbiased, _ = finalize_moments(m)
+    with torch.no_grad():
+        layer.log_scale.data.copy_(torch.log(torch.sqrt(var_unbiased) + layer.eps).float().view(layer.dimensions))
+        layer.bias.data.copy_(mean.float().view(layer.dimensions))
+    layer.initialized = True
+    return layer
+
+
+def batchnorm_stats_sharded(layer, x_local, group=None):
+    """Train-mode statistics of the flow BatchNorm (modules.py:285-294) from the global batch: batch_mean / batch_var
+    (+eps) and the running-statistics update, identical on every rank."""
+    m = channel_moments(x_local)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group)
+    mean, var_biased, _, _ = finalize_moments(m)
+    with torch.no_grad():
+        layer.batch_mean.copy_(mean.float().view(layer.dimensions))
+        layer.batch_var.copy_((var_biased.float() + layer.eps).view(layer.dimensions))
+        layer.running_mean.mul_(1.0 - layer.momentum).add_(layer.batch_mean * layer.momentum)
+        layer.running_var.mul_(1.0 - layer.momentum).add_(layer.batch_var * layer.momentum)
+    return layer

@@ -599,3 +599,25 @@ def test_flowpp_conditioner_kernel_vs_oracle(dims, masking, K, B):
     print('flow++ conditioner err vs fp64: kernel %.3e | torch-gpu %.3e | cpu fp32 %.3e | scale %.2f' % (e_f, e_l, e_r, scale))
     close(fused, ref, rtol=2e-5, atol=5e-6 * scale, what='fused flow++ conditioner vs oracle')
     assert e_f <= 6.0 * max(e_r, e_l) + 1e-6 * scale
+
+
+def test_sharded_statistics_match_global_batch():
+    """ActNorm init / BatchNorm train statistics from per-shard moments (what the ranks all-reduce) == full-batch pass."""
+    n = nfb()
+    from nfb200 import parallel
+    torch.manual_seed(0)
+    x = (torch.randn(10, 12, 4, 4) * 1.7 + 0.3).to(DEV)
+    ref = n.flows.ActNorm((12, 4, 4)).to(DEV)
+    ref(x, torch.zeros(10, device=DEV))  # single-process data-dependent init
+    m = parallel.channel_moments(x[:3].contiguous()) + parallel.channel_moments(x[3:].contiguous())  # = all-reduce(SUM)
+    mean, var_b, var_u, cnt = parallel.finalize_moments(m)
+    assert float(cnt) == 160.0
+    close(torch.log(torch.sqrt(var_u) + 1e-5).float(), ref.log_scale.view(-1), rtol=1e-6, atol=1e-6)
+    close(mean.float(), ref.bias.view(-1), rtol=1e-6, atol=1e-6)
+    sharded = parallel.actnorm_init_sharded(n.flows.ActNorm((12, 4, 4)).to(DEV), x)  # world size 1: no collective
+    close(sharded.log_scale, ref.log_scale, rtol=1e-6, atol=1e-6)
+    bn = n.flows.BatchNorm((12, 4, 4), affine=False).to(DEV).train()
+    bn(x, torch.zeros(10, device=DEV))
+    bn2 = parallel.batchnorm_stats_sharded(n.flows.BatchNorm((12, 4, 4), affine=False).to(DEV), x)
+    close(bn2.batch_var, bn.batch_var, rtol=1e-6, atol=1e-6)
+    close(bn2.running_mean, bn.running_mean, rtol=1e-6, atol=1e-6)
