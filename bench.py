@@ -433,6 +433,33 @@ def run_nfb200(args, rank, world, local_rank):
         e2e_ms = timed(n_str, host_ring, True)
         e2e_value = batch * world * args.steps / (e2e_ms * 1e-3)
 
+        # ---- inverse direction (sampling, main.py:109-116): z -> y, one batch in flight, graph replay ----------------
+        inv = None
+        try:
+            zs = torch.randn_like(dev_ring[0])
+            st = lanes[0]['stream']
+            with torch.cuda.stream(st):
+                for _ in range(2):
+                    net.backward(zs)
+            st.synchronize()
+            ginv = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ginv, stream=st):
+                yinv, linv = net.backward(zs)
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    ginv.replay()
+                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                i0.record(st)
+                for _ in range(max(3, args.steps // 2)):
+                    ginv.replay()
+                i1.record(st)
+            st.synchronize()
+            inv_ms = i0.elapsed_time(i1) / max(3, args.steps // 2)
+            inv = {'value': batch * world / (inv_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': inv_ms,
+                   'note': 'model.backward(z) (inverse + log-det), one batch in flight per GPU'}
+        except Exception as e:  # never take the bench line down
+            inv = {'error': repr(e)}
+
         # ---- bits/dim of the (global) batch ring[0] ------------------------------------------------------
         x_static.copy_(dev_ring[0])
         graph.replay()
@@ -487,7 +514,7 @@ def run_nfb200(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'h2d_bytes_per_step': bytes_per_batch, 'd2h_bytes_per_step': 16 + 4 * batch},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'clocks': clocks, 'roofline': roof, 'conditioner_kernels': dom, 'cpu_baseline': cpu,
+        'inverse': inv, 'clocks': clocks, 'roofline': roof, 'conditioner_kernels': dom, 'cpu_baseline': cpu,
         'bits_per_dim': {'gpu_global_batch': bpd_global, 'gpu_rank0_batch': bpd_local, 'gpu_on_cpu_sample': bpd_gpu_sample,
                          'cpu_oracle_on_sample': bpd_cpu,
                          'rel_err': abs(bpd_gpu_sample - bpd_cpu) / abs(bpd_cpu), 'tolerance': 1e-5},

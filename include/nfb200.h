@@ -154,6 +154,12 @@ int nfb_actnorm_invconv_fwd(const float* z_in, float* z_out, const float* ldj_in
                             const float* log_scale, const float* bias, const float* W, const float* log_s, int B, int C,
                             int HW, nfb_stream_t stream);
 
+/* Inverse of that pair in one pass: InvertibleConv1x1.backward (modules.py:484-497, Winv from nfb_invconv1x1_weight)
+ * followed by ActNorm.backward (modules.py:252-256) -- bit-identical to the two calls back to back. */
+int nfb_invconv_actnorm_inv(const float* y_in, float* y_out, const float* ldj_in, float* ldj_out, const float* Winv,
+                            const float* log_s, const float* log_scale, const float* bias, int B, int C, int HW,
+                            nfb_stream_t stream);
+
 /* ---------------- Squeeze2d / Unsqueeze2d (squeeze.py:153-189) ---------------- */
 
 /* (B,C,H,W) -> (B,4C,H/2,W/2): out[b,4c+2dy+dx,i,j] = in[b,c,2i+dy,2j+dx]; odd swaps the two channel halves. */

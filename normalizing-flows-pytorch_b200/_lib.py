@@ -44,6 +44,7 @@ _SIGNATURES = {
     'nfb_invconv1x1_weight': [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     'nfb_invconv1x1_apply': [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
     'nfb_actnorm_invconv_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_invconv_actnorm_inv': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'nfb_squeeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nfb_unsqueeze2d': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nfb_gauss_nll': [_P, _P, _P, _P, _I, _I, _P],

@@ -105,7 +105,7 @@ __device__ __forceinline__ void load_m(float (&m)[OCG], const float* p) {
     }
 }
 
-template <int OCG, bool ACTNORM>
+template <int OCG, int ACTNORM>
 __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restrict__ zin, float* __restrict__ zout,
                                                           const float* ldj_in, float* ldj_out,
                                                           const float* __restrict__ M, const float* __restrict__ log_s,
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
     for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
         const int ci = i / tpv, pv = i - ci * tpv;
         float4 v = ldg4(zb + static_cast<size_t>(ci) * HW + 4 * pv);
-        if (ACTNORM) {
+        if (ACTNORM == 1) {
             const float e = expf(__ldg(an_log_scale + ci)), bi = __ldg(an_bias + ci);
             v.x = __fdiv_rn(__fsub_rn(v.x, bi), e);
             v.y = __fdiv_rn(__fsub_rn(v.y, bi), e);
@@ -142,14 +142,17 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
         float part = 0.f, an = 0.f;
         for (int c = threadIdx.x; c < C; c += 32) {
             part += __ldg(log_s + c);
-            if (ACTNORM) an -= __ldg(an_log_scale + c);
+            if (ACTNORM == 1) an -= __ldg(an_log_scale + c);
+            if (ACTNORM == 2) an += __ldg(an_log_scale + c);
         }
         part = warp_sum(part);
         if (ACTNORM) an = warp_sum(an);
         if (threadIdx.x == 0) {
             float l = ldj_in[b];
-            if (ACTNORM) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
-            ldj_out[b] = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+            if (ACTNORM == 1) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));     // ActNorm.forward first
+            l = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+            if (ACTNORM == 2) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));     // ActNorm.backward after the conv
+            ldj_out[b] = l;
         }
     }
     __syncthreads();
@@ -177,11 +180,18 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
         }
         float* ob = zout + (static_cast<size_t>(b) * C + og * OCG) * HW + p0 + 4 * pv;
 #pragma unroll
-        for (int o = 0; o < OCG; ++o) st4(ob + static_cast<size_t>(o) * HW, make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
+        for (int o = 0; o < OCG; ++o) {
+            if (ACTNORM == 2) {  // ActNorm.backward (modules.py:253): y * exp(log_scale) + bias
+                const float e = expf(__ldg(an_log_scale + og * OCG + o)), bi = __ldg(an_bias + og * OCG + o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[o][q] = __fadd_rn(__fmul_rn(acc[o][q], e), bi);
+            }
+            st4(ob + static_cast<size_t>(o) * HW, make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
+        }
     }
 }
 
-template <int OCG, bool ACTNORM>
+template <int OCG, int ACTNORM>
 static int launch_tiled(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
                         const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
                         cudaStream_t st) {
@@ -202,7 +212,7 @@ static int launch_tiled(const float* zin, float* zout, const float* ldj_in, floa
     return launch_status();
 }
 
-template <bool ACTNORM>
+template <int ACTNORM>
 static int apply_dispatch(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
                           const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
                           cudaStream_t st) {
@@ -238,7 +248,7 @@ extern "C" int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    const int rc = apply_dispatch<false>(z_in, z_out, ldj_in, ldj_out, M, log_s, nullptr, nullptr, sign, B, C, HW, st);
+    const int rc = apply_dispatch<0>(z_in, z_out, ldj_in, ldj_out, M, log_s, nullptr, nullptr, sign, B, C, HW, st);
     if (rc != -100) return rc;
     const long long total = static_cast<long long>(B) * C * HW;
     long long blocks = (total + 255) / 256;
@@ -255,7 +265,18 @@ extern "C" int nfb_actnorm_invconv_fwd(const float* z_in, float* z_out, const fl
     if (!z_in || !z_out || !ldj_in || !ldj_out || !log_scale || !bias || !W || !log_s) return NFB_ERR_NULL;
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
-    const int rc = apply_dispatch<true>(z_in, z_out, ldj_in, ldj_out, W, log_s, log_scale, bias, 1.f, B, C, HW,
+    const int rc = apply_dispatch<1>(z_in, z_out, ldj_in, ldj_out, W, log_s, log_scale, bias, 1.f, B, C, HW,
                                         as_stream(stream));
     return rc == -100 ? NFB_ERR_UNSUPPORTED : rc;  // caller runs the two layers separately for odd shapes
+}
+
+extern "C" int nfb_invconv_actnorm_inv(const float* y_in, float* y_out, const float* ldj_in, float* ldj_out,
+                                       const float* Winv, const float* log_s, const float* log_scale, const float* bias,
+                                       int B, int C, int HW, nfb_stream_t stream) {
+    if (!y_in || !y_out || !ldj_in || !ldj_out || !Winv || !log_s || !log_scale || !bias) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    if (y_in == y_out) return NFB_ERR_UNSUPPORTED;
+    const int rc = apply_dispatch<2>(y_in, y_out, ldj_in, ldj_out, Winv, log_s, log_scale, bias, -1.f, B, C, HW,
+                                     as_stream(stream));
+    return rc == -100 ? NFB_ERR_UNSUPPORTED : rc;
 }

@@ -209,6 +209,20 @@ def _actnorm_invconv(an, conv, z, log_df_dz):
     return out, log_df_dz
 
 
+def _invconv_actnorm_inv(an, conv, y, log_df_dz):
+    """InvertibleConv1x1.backward + ActNorm.backward as one launch; None if the shape needs the separate kernels."""
+    y, log_df_dz = L.dev(y, 'y'), L.dev(log_df_dz, 'log_df_dz')
+    B, C, HW = _bchw(y)
+    out = torch.empty_like(y)
+    rc = L.lib().nfb_invconv_actnorm_inv(L.ptr(y), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz),
+                                         L.ptr(conv.matrices()[1]), L.ptr(conv.log_s.data), L.ptr(an.log_scale.data),
+                                         L.ptr(an.bias.data), B, C, HW, L.stream())
+    if rc == L.ERR_UNSUPPORTED:
+        return None
+    L.check(rc)
+    return out, log_df_dz
+
+
 def _glow_step(an, conv, cpl, z, log_df_dz):
     """ActNorm -> InvertibleConv1x1 -> AffineCoupling (ConvNet conditioner) as ONE launch; None if not applicable."""
     from .coupling import AffineCoupling
@@ -263,8 +277,20 @@ class Compose(nn.Module):
         return z, log_df_dz
 
     def backward(self, z, log_df_dz):
-        for layer in reversed(self.layers):
+        layers = self.layers
+        i = len(layers) - 1
+        while i >= 0:
+            layer = layers[i]
+            # peephole (mirror of forward): 1x1 conv inverse followed by the ActNorm inverse as one kernel
+            if (i >= 1 and type(layer) is InvertibleConv1x1 and type(layers[i - 1]) is ActNorm and layers[i - 1].initialized
+                    and self.fuse_steps):
+                out = _invconv_actnorm_inv(layers[i - 1], layer, z, log_df_dz)
+                if out is not None:
+                    z, log_df_dz = out
+                    i -= 2
+                    continue
             z, log_df_dz = layer.backward(z, log_df_dz)
+            i -= 1
         return z, log_df_dz
 
     inverse = backward

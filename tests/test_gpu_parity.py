@@ -409,9 +409,12 @@ def test_fused_actnorm_invconv_is_bit_identical():
         x = torch.randn((5, ) + dims, device=DEV)
         l0 = torch.randn(5, device=DEV)
         z1, l1 = comp(x, l0.clone())
+        y1, m1 = comp.backward(z1, l1.clone())
         comp.fuse_steps = 0
         z2, l2 = comp(x, l0.clone())
         assert torch.equal(z1, z2) and torch.equal(l1, l2), dims
+        y2, m2 = comp.backward(z1, l1.clone())
+        assert torch.equal(y1, y2) and torch.equal(m1, m2), dims  # fused inverse == separate inverse layers
 
 
 @pytest.mark.parametrize('key,values,cin,cout,hw', [(0, (0, 1), 6, 12, 16), (1, (0, 1, 2, 3), 24, 48, 8),
