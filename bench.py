@@ -296,6 +296,31 @@ def dominant_kernel_probe(net, batch, clocks):
     return out
 
 
+def train_probe(net, dev_ring, batch, world, steps):
+    """Training step of main.py:78-92 on the new path: train-mode forward (bijection kernels + cuDNN/cuBLAS conditioner),
+    loss = global mean NLL, backward through csrc/backward.cu, flat-bucket gradient all-reduce, Adam.  Eager (no graph);
+    runs on a deep copy so the benchmarked weights are untouched.  Informational: the headline metric is fwd+logdet."""
+    import copy
+    import nfb200
+    from nfb200 import parallel
+    tnet = copy.deepcopy(net).train()
+    opt = torch.optim.Adam(tnet.parameters(), lr=1e-4)
+    losses = [parallel.train_step(tnet, opt, dev_ring[i % len(dev_ring)]) for i in range(2)]
+    torch.cuda.synchronize()
+    n0 = nfb200._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses.append(parallel.train_step(tnet, opt, dev_ring[(2 + i) % len(dev_ring)]))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': batch * world / (ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms,
+            'nfb200_launches_per_step': (nfb200._lib.launch_count() - n0) // steps, 'loss_first': losses[0],
+            'loss_last': losses[-1],
+            'note': 'train-mode fwd + backward kernels + gradient all-reduce + Adam, eager; conditioner fwd/bwd on cuDNN'}
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -468,6 +493,14 @@ def run_nfb200(args, rank, world, local_rank):
         bpd_global = parallel.global_bits_per_dim(total, D)
         torch.cuda.synchronize()
 
+    # ---- training step; every rank takes part (gradient all-reduce) ------------------------------
+    train = None
+    if not args.no_train and (world == 1 or args.train):
+        try:
+            train = train_probe(net, dev_ring, batch, world, max(2, min(5, args.steps // 4)))
+        except Exception as e:  # never take the bench line down (N > 1: opt-in, a failing rank would stall the others)
+            train = {'error': repr(e)}
+
     if rank != 0:
         return
 
@@ -514,7 +547,7 @@ def run_nfb200(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'h2d_bytes_per_step': bytes_per_batch, 'd2h_bytes_per_step': 16 + 4 * batch},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'inverse': inv, 'clocks': clocks, 'roofline': roof, 'conditioner_kernels': dom, 'cpu_baseline': cpu,
+        'inverse': inv, 'train_step': train, 'clocks': clocks, 'roofline': roof, 'conditioner_kernels': dom, 'cpu_baseline': cpu,
         'bits_per_dim': {'gpu_global_batch': bpd_global, 'gpu_rank0_batch': bpd_local, 'gpu_on_cpu_sample': bpd_gpu_sample,
                          'cpu_oracle_on_sample': bpd_cpu,
                          'rel_err': abs(bpd_gpu_sample - bpd_cpu) / abs(bpd_cpu), 'tolerance': 1e-5},
@@ -548,6 +581,8 @@ def main():
     ap.add_argument('--impl', default='nfb200', choices=['nfb200', 'reference'])
     ap.add_argument('--workload', default='glow32', choices=sorted(WORKLOADS))
     ap.add_argument('--streams', type=int, default=3, help='batches in flight (one CUDA graph + stream each)')
+    ap.add_argument('--train', action='store_true', help='also time the training step when N > 1 (default: N = 1 only)')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step probe')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'nfb200' else args.warmup
 

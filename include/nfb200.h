@@ -93,7 +93,8 @@ int nfb_rqs_coupling_inv(const float* z_in, float* z_out, const float* params, c
                          nfb_stream_t stream);
 
 /* squeeze (split) / unsqueeze (merge) of AbstractCoupling (coupling.py:33,35): bit-exact permutations.
- * z0_out / z1_out are (B, c0, h, w) contiguous; either may be NULL to skip it. */
+ * z0_out / z1_out are (B, c0, h, w) contiguous; either may be NULL to skip it (merge: a NULL half reads as zeros --
+ * the gradient of a split of which only one half was used). */
 int nfb_coupling_split(const float* z, float* z0_out, float* z1_out, int B, int C, int H, int W, int mode,
                        int odd, nfb_stream_t stream);
 int nfb_coupling_merge(const float* z0, const float* z1, float* z_out, int B, int C, int H, int W, int mode,
@@ -143,7 +144,7 @@ int nfb_logit_inv(const float* z_in, float* z_out, const float* ldj_in, float* l
 int nfb_invconv1x1_weight(const float* P, const float* L, const float* U, const float* log_s,
                           const float* sign_s, float* W_out, float* Winv_out, int C, nfb_stream_t stream);
 /* out[b,:,p] = M @ z[b,:,p]; ldj += sign * sum(log_s) * HW.  forward: M = W, sign = +1 (modules.py:477-480);
- * inverse: M = W^-1, sign = -1 (modules.py:490-495).  z_out must NOT alias z_in. */
+ * inverse: M = W^-1, sign = -1 (modules.py:490-495).  z_out must NOT alias z_in.  ldj_out == NULL: matrix apply only. */
 int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
                          const float* log_s, float sign, int B, int C, int HW, nfb_stream_t stream);
 
@@ -222,6 +223,55 @@ int nfb_flowpp_cond_fwd(const float* const* tensors, const float* src, float* pa
  * mode < 0: src = (B, in_ch). */
 int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd, int in_ch,
                 int out_ch, nfb_stream_t stream);
+
+/* ---------------- gradients of the bijective layers (the reference gets them from autograd) -------
+ * Convention: gy = dLoss/d(z_out) (layout of z), gldj = dLoss/d(ldj_out) (device float[B], may be NULL = zeros).  Every
+ * layer passes gldj through unchanged to its ldj input, so only gz and the parameter gradients are produced.  Each
+ * backward recomputes tanh/exp from the layer's saved INPUT.  `scratch`: device doubles (sizes below), zeroed by the
+ * call; batch-wide sums are accumulated in fp64 and rounded to fp32 once. */
+
+/* AffineCoupling.forward (coupling.py:104-112): gz (z0 slots: gy*exp(s), z1 slots: gy -- the conditioner's own
+ * gradient wrt z1 is added by the caller), gparams (B, 2*c0, h, w) = [gy0 | gs*a*(1-tanh^2)], gs = gy0*z0*exp(s)+gldj,
+ * g_s_log_scale = sum gs*tanh(s_raw), g_s_bias = sum gs (device scalars, may be NULL).  scratch: 2 doubles. */
+int nfb_affine_coupling_bwd(const float* z_in, const float* params, const float* gy, const float* gldj, float* gz,
+                            float* gparams, float* g_s_log_scale, float* g_s_bias, double* scratch,
+                            const float* s_log_scale, const float* s_bias, int B, int C, int H, int W, int mode, int odd,
+                            nfb_stream_t stream);
+/* MixLogAttnCoupling.forward (coupling.py:172-190): gparams (B, (2+3K)*c0, h, w) in the layout of params; the mixture
+ * responsibilities are evaluated in the log domain (no division by an underflowed density).  scratch: 2 doubles. */
+int nfb_mixlog_coupling_bwd(const float* z_in, const float* params, const float* gy, const float* gldj, float* gz,
+                            float* gparams, float* g_a_log_scale, float* g_a_bias, double* scratch,
+                            const float* a_log_scale, const float* a_bias, int B, int C, int H, int W, int mode, int odd,
+                            int K, nfb_stream_t stream);
+/* RQ-spline coupling, forward direction (nfb_rqs_coupling_fwd): gparams (B, (3K-1)*c0, h, w). */
+int nfb_rqs_coupling_bwd(const float* z_in, const float* params, const float* gy, const float* gldj, float* gz,
+                         float* gparams, int B, int C, int H, int W, int mode, int odd, int K, float bound,
+                         nfb_stream_t stream);
+/* ActNorm.forward (modules.py:246-250): gz = gy/exp(log_scale); g_bias[c] = -sum gz; g_log_scale[c] = -sum gy*y -
+ * HW*sum_b gldj[b].  scratch: 2C doubles. */
+int nfb_actnorm_bwd(const float* gy, const float* z_in, const float* gldj, const float* log_scale, const float* bias,
+                    float* gz, float* g_log_scale, float* g_bias, double* scratch, int B, int C, int HW,
+                    nfb_stream_t stream);
+/* flow BatchNorm.forward (modules.py:300-305) with mean/var treated as constants -- the reference copies the batch
+ * statistics into buffers through .data (modules.py:288-289), so autograd never sees them.  gx = gy*exp(log_gamma)/
+ * sqrt(var); g_log_gamma[c] = sum gy*xhat*exp(log_gamma) + HW*sum_b gldj[b]; g_beta[c] = sum gy (either may be NULL:
+ * affine=False).  scratch: 2C doubles. */
+int nfb_bnflow_bwd(const float* gy, const float* x_in, const float* gldj, const float* mean, const float* var,
+                   const float* log_gamma, float* gx, float* g_log_gamma, float* g_beta, double* scratch, int B, int C,
+                   int HW, nfb_stream_t stream);
+/* InvertibleConv1x1.forward (modules.py:470-482).  gz = W^T gy is nfb_invconv1x1_apply(gy, gz, NULL, NULL, W^T, ...);
+ * gW[i,j] = sum_{b,p} gy[b,i,p] z[b,j,p] (C*C floats, zeroed by the call, fp32 atomics across position chunks). */
+int nfb_invconv1x1_wgrad(const float* gy, const float* z_in, float* gW, int B, int C, int HW, nfb_stream_t stream);
+/* chain rule through W = P (L o tril + I)(U o triu + diag(sign_s exp(log_s))) (modules.py:471-473) plus the log-det
+ * term: gL, gU (C*C, zero outside the strict triangles), g_log_s (C). */
+int nfb_invconv1x1_weight_bwd(const float* gW, const float* P, const float* L, const float* U, const float* log_s,
+                              const float* sign_s, const float* gldj, float* gL, float* gU, float* g_log_s, int B, int C,
+                              int HW, nfb_stream_t stream);
+/* Logit.forward (modules.py:146-150): gx = gy/(x(1-x)) + gldj[b]*(1/(1-x) - 1/x) inside [lo, hi], 0 outside (clamp). */
+int nfb_logit_bwd(const float* x_in, const float* gy, const float* gldj, float* gx, float lo, float hi, int B, int D,
+                  nfb_stream_t stream);
+/* nfb_gauss_nll rows: gz = z * g_rows[b], gldj = -g_rows[b] (gldj may be NULL). */
+int nfb_gauss_nll_bwd(const float* z, const float* g_rows, float* gz, float* gldj, int B, int D, nfb_stream_t stream);
 
 #ifdef __cplusplus
 }

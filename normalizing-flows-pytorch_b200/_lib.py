@@ -57,6 +57,15 @@ _SIGNATURES = {
     'nfb_pack_conv3x3': [_P, _P, _I, _I, _P],
     'nfb_flowpp_cond_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_affine_coupling_bwd': [_P] * 11 + [_I] * 6 + [_P],
+    'nfb_mixlog_coupling_bwd': [_P] * 11 + [_I] * 7 + [_P],
+    'nfb_rqs_coupling_bwd': [_P] * 6 + [_I] * 7 + [_F, _P],
+    'nfb_actnorm_bwd': [_P] * 9 + [_I, _I, _I, _P],
+    'nfb_bnflow_bwd': [_P] * 10 + [_I, _I, _I, _P],
+    'nfb_invconv1x1_wgrad': [_P, _P, _P, _I, _I, _I, _P],
+    'nfb_invconv1x1_weight_bwd': [_P] * 10 + [_I, _I, _I, _P],
+    'nfb_logit_bwd': [_P, _P, _P, _P, _F, _F, _I, _I, _P],
+    'nfb_gauss_nll_bwd': [_P, _P, _P, _P, _I, _I, _P],
 }
 _RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong}
 

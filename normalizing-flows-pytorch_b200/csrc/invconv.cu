@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) invconv_apply_scalar(const float* __restr
                                                            const float* ldj_in, float* ldj_out,
                                                            const float* __restrict__ M, const float* __restrict__ log_s,
                                                            float sign, int B, int C, int HW) {
-    if (static_cast<long long>(blockIdx.x) * blockDim.x < B) {
+    if (ldj_out && static_cast<long long>(blockIdx.x) * blockDim.x < B) {
         float part = 0.f;
         for (int c = threadIdx.x & 31; c < C; c += 32) part += __ldg(log_s + c);
         part = warp_sum(part);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
         }
         st4(zs + ci * TP + 4 * pv, v);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
+    if (ldj_out && blockIdx.x == 0 && threadIdx.x < 32) {
         float part = 0.f, an = 0.f;
         for (int c = threadIdx.x; c < C; c += 32) {
             part += __ldg(log_s + c);
@@ -244,7 +244,8 @@ extern "C" int nfb_invconv1x1_weight(const float* P, const float* L, const float
 extern "C" int nfb_invconv1x1_apply(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out,
                                     const float* M, const float* log_s, float sign, int B, int C, int HW,
                                     nfb_stream_t stream) {
-    if (!z_in || !z_out || !ldj_in || !ldj_out || !M || !log_s) return NFB_ERR_NULL;
+    if (!z_in || !z_out || !M) return NFB_ERR_NULL;
+    if (ldj_out && (!ldj_in || !log_s)) return NFB_ERR_NULL;  // ldj_out == NULL: plain matrix apply (the gradient W^T gy)
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);

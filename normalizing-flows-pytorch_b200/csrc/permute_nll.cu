@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) split_merge_kernel(const float* zfull_in,
             if (first) { if (h0_out) h0_out[hoff] = v; }
             else       { if (h1_out) h1_out[hoff] = v; }
         } else {
-            zfull_out[i] = first ? h0_in[hoff] : h1_in[hoff];
+            zfull_out[i] = first ? (h0_in ? h0_in[hoff] : 0.f) : (h1_in ? h1_in[hoff] : 0.f);  // NULL half -> zeros
         }
     }
 }
@@ -198,7 +198,7 @@ extern "C" int nfb_coupling_split(const float* z, float* z0_out, float* z1_out, 
 }
 extern "C" int nfb_coupling_merge(const float* z0, const float* z1, float* z_out, int B, int C, int H, int W, int mode,
                                   int odd, nfb_stream_t stream) {
-    if (!z0 || !z1 || !z_out) return NFB_ERR_NULL;
+    if ((!z0 && !z1) || !z_out) return NFB_ERR_NULL;
     return launch_split_merge<true>(nullptr, z_out, z0, z1, nullptr, nullptr, B, C, H, W, mode, odd, stream);
 }
 

@@ -1,7 +1,9 @@
 """Conditioner networks of the couplings (modules.py:342-438, 500-578), same state_dict keys as the reference.
 
 ``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
--> out_block (BN, ReLU, WN-layer).  Eval mode only (running statistics).
+-> out_block (BN, ReLU, WN-layer).  Eval mode without autograd: ONE fused kernel over folded weights.  Train mode (batch
+statistics, modules.py:349-352) or with gradients recorded: the same network as cuDNN / cuBLAS ops under torch autograd
+(``_forward_autograd``) -- a native train-mode conditioner is the next step of SURVEY.md 8f.
 """
 import ctypes
 
@@ -83,13 +85,16 @@ class _ResNetConditioner(nn.Module):
             self._pack_key = key
         return self._pack
 
-    def _check_mode(self):
+    def _fused_ok(self, x):
+        """The fused kernel is the eval-mode inference path; train mode and autograd go through torch ops."""
         if self.training:
-            raise RuntimeError('nfb200 conditioners implement the eval-mode (running statistics) path only')
+            return False
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
 
     def forward(self, x):
         """params = net(x) for an explicit conditioner input x: (B, in, h, w) or (B, in)."""
-        self._check_mode()
+        if not self._fused_ok(x):
+            return self._forward_autograd(x)
         x = L.dev(x, 'conditioner input')
         B = x.size(0)
         if self.conv:
@@ -108,7 +113,8 @@ class _ResNetConditioner(nn.Module):
 
     def forward_from_z(self, z, mode, odd):
         """params = net(z1) with z1 (the pass-through half of the coupling split) gathered inside the kernel."""
-        self._check_mode()
+        if not self._fused_ok(z):
+            return None
         B = z.size(0)
         if self.conv:
             _, C, H, W = z.shape
@@ -139,7 +145,6 @@ class _ResNetConditioner(nn.Module):
         return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
 
     def _forward_library(self, x):
-        self._check_mode()
         x = L.dev(x, 'conditioner input')
         with torch.no_grad():
             x = self._layer(self.in_block[0], x)
@@ -151,6 +156,28 @@ class _ResNetConditioner(nn.Module):
                 x = x + y
             x = self._bn_relu(self.out_block[0], x)
             return self._layer(self.out_block[2], x)
+
+
+    # -- train mode / autograd: torch ops with the reference's semantics (batch statistics + running-stat update by the
+    #    nn.BatchNorm modules, WeightNorm recomputed differentiably as in weight_norm.py:40) ---------------------------
+    def _wn_apply(self, wn, x):
+        v, g = wn.module.weight_v, wn.module.weight_g
+        w = v * (g / (torch.norm(v, dim=0) + wn.eps)).expand_as(v)
+        if self.conv:
+            return F.conv2d(x, w, wn.module.bias, 1, (w.size(2) - 1) // 2)
+        return F.linear(x, w, wn.module.bias)
+
+    def _forward_autograd(self, x):
+        x = L.dev(x, 'conditioner input')
+        x = self._wn_apply(self.in_block[0], x)
+        for blk in self.mid_block:
+            y = F.relu(blk.net[0](x))
+            y = self._wn_apply(blk.net[2], y)
+            y = F.relu(blk.net[3](y))
+            y = self._wn_apply(blk.net[5], y)
+            x = x + y
+        x = F.relu(self.out_block[0](x))
+        return self._wn_apply(self.out_block[2], x)
 
 
 class MLP(_ResNetConditioner):

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from . import autograd as G
 from .conditioner import MLP, ConvNet, GatedAttn, GatedConv2d, GatedLinear
 from .squeeze import coupling_split
 
@@ -44,19 +45,31 @@ class AbstractCoupling(nn.Module):
             return z.size(0), z.size(1), 1, 1
         return tuple(z.shape)
 
-    def _params(self, z):
-        net = self.net
+    def _params(self, z, net=None):
+        net = self.net if net is None else net
         if hasattr(net, 'forward_from_z'):  # fused conditioner: gathers z1 from z inside the kernel
             p = net.forward_from_z(z, self.mode, self.odd)
             if p is not None:
                 return p
-        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
+        # train mode / autograd: z1 is materialised (its gradient is scattered back by SplitHalfFn)
+        z1 = self._z1(z)
         return L.dev(net(z1), 'conditioner output')
+
+    def _z1(self, z):
+        if G.needs_grad(z):
+            return G.SplitHalfFn.apply(z, self.mode, self.odd)
+        return coupling_split(z, self.mode, self.odd, want_z0=False)[1]
+
+    def _recording(self, z, ldj):
+        """True when this call has to be differentiable (any input or parameter of the layer requires grad)."""
+        return torch.is_grad_enabled() and (z.requires_grad or ldj.requires_grad
+                                            or any(p.requires_grad for p in self.parameters()))
 
     def forward(self, z, log_df_dz):
         return self._run(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), False)
 
     def backward(self, y, log_df_dz):
+        """Inverse direction: inference kernels only (the reference samples under no_grad, main.py:121-124)."""
         return self._run(L.dev(y, 'y'), L.dev(log_df_dz, 'log_df_dz'), True)
 
     inverse = backward
@@ -70,16 +83,11 @@ class AdditiveCoupling(AbstractCoupling):
         in_chs, out_chs = self._half_channels()
         self.net_t = MLP(in_chs, out_chs) if len(dims) == 1 else ConvNet(in_chs, out_chs)
 
-    def _params(self, z):
-        p = self.net_t.forward_from_z(z, self.mode, self.odd)
-        if p is not None:
-            return p
-        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
-        return L.dev(self.net_t(z1), 'conditioner output')
-
     def _run(self, z, ldj, inverse):
+        if not inverse and self._recording(z, ldj):
+            raise NotImplementedError('nfb200: AdditiveCoupling has no gradient kernel (no model of the reference uses it)')
         B, C, H, W = self._geom(z)
-        t = self._params(z)
+        t = self._params(z, self.net_t)
         out = torch.empty_like(z)
         L.check(L.lib().nfb_additive_coupling(L.ptr(z), L.ptr(out), L.ptr(t), -1.0 if inverse else 1.0, B, C, H, W,
                                               self.mode, int(self.odd), L.stream()))
@@ -99,6 +107,8 @@ class AffineCoupling(AbstractCoupling):
     def _run(self, z, ldj, inverse):
         B, C, H, W = self._geom(z)
         params = self._params(z)
+        if not inverse and self._recording(z, ldj):
+            return G.AffineCouplingFn.apply(z, params, ldj, self.s_log_scale, self.s_bias, self.mode, self.odd)
         out = torch.empty_like(z)
         fn = L.lib().nfb_affine_coupling_inv if inverse else L.lib().nfb_affine_coupling_fwd
         L.check(fn(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj), L.ptr(self.s_log_scale.data),
@@ -159,7 +169,7 @@ class MixLogAttnCoupling(AbstractCoupling):
         return super()._apply(fn, *a, **k)
 
     def _params(self, z):
-        if z.dim() == 4 and not self.net.training and self.fused_conditioner:
+        if z.dim() == 4 and not self.net.training and self.fused_conditioner and not self._recording(z, z):
             B, C, H, W = z.shape
             h, w = (H // 2, W // 2) if self.mode == L.SPLIT_CHECKER else (H, W)
             n_out = sum(self.sections)
@@ -170,16 +180,18 @@ class MixLogAttnCoupling(AbstractCoupling):
             if rc != L.ERR_UNSUPPORTED:
                 L.check(rc)
                 return out
-        # library path (torch ops on the device): 1-D inputs and spatial sizes the kernel does not cover
-        _, z1 = coupling_split(z, self.mode, self.odd, want_z0=False)
-        with torch.no_grad():
-            return L.dev(self.net(z1), 'conditioner output')
+        # library path (torch ops on the device): 1-D inputs, spatial sizes the kernel does not cover, train mode
+        z1 = self._z1(z)
+        return L.dev(self.net(z1), 'conditioner output')
 
     fused_conditioner = True
 
     def _run(self, z, ldj, inverse):
         B, C, H, W = self._geom(z)
         params = self._params(z)
+        if not inverse and self._recording(z, ldj):
+            return G.MixLogCouplingFn.apply(z, params, ldj, self.a_log_scale, self.a_bias, self.mode, self.odd,
+                                            self.n_mixtures)
         out = torch.empty_like(z)
         ldj_out = torch.empty_like(ldj)  # MixLogCDF / Logit return new log-det tensors (modules.py:194,150)
         if not inverse:
@@ -213,6 +225,8 @@ class RQSplineCoupling(AbstractCoupling):
     def _run(self, z, ldj, inverse):
         B, C, H, W = self._geom(z)
         params = self._params(z)
+        if not inverse and self._recording(z, ldj):
+            return G.RQSCouplingFn.apply(z, params, ldj, self.mode, self.odd, self.n_bins, self.tail_bound)
         out = torch.empty_like(z)
         fn = L.lib().nfb_rqs_coupling_inv if inverse else L.lib().nfb_rqs_coupling_fwd
         L.check(fn(L.ptr(z), L.ptr(out), L.ptr(params), L.ptr(ldj), L.ptr(ldj), B, C, H, W, self.mode, int(self.odd),

@@ -2,13 +2,16 @@
 
 Same class names, constructor signatures, ``forward(z, log_df_dz)`` / ``backward(y, log_df_dz)`` methods and
 ``state_dict`` keys as the reference, so reference checkpoints load unchanged.  ``inverse`` is an
-alias of ``backward``.  Inference only: the kernels have no autograd.
+alias of ``backward``.  ``forward`` is differentiable (``flows/autograd.py``: one gradient kernel per layer) whenever
+gradients are enabled and an input or parameter requires them; the inverse direction is inference-only, like the
+reference's sampling path (main.py:121-124 runs it under no_grad).
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from . import autograd as G
 
 
 def _bchw(z):
@@ -25,11 +28,13 @@ class Logit(nn.Module):
         self.eps = eps
 
     def forward(self, x, log_df_dz):
+        # torch.clamp(x, eps, 1.0 - eps) rounds the python doubles to fp32 (modules.py:147)
+        lo, hi = float(np.float32(self.eps)), float(np.float32(1.0 - self.eps))
+        if G.needs_grad(x, log_df_dz):
+            return G.LogitFn.apply(x, log_df_dz, lo, hi)
         x, log_df_dz = L.dev(x, 'x'), L.dev(log_df_dz, 'log_df_dz')
         out, ldj = torch.empty_like(x), torch.empty_like(log_df_dz)
         B = x.size(0)
-        # torch.clamp(x, eps, 1.0 - eps) rounds the python doubles to fp32 (modules.py:147)
-        lo, hi = float(np.float32(self.eps)), float(np.float32(1.0 - self.eps))
         L.check(L.lib().nfb_logit_fwd(L.ptr(x), L.ptr(out), L.ptr(log_df_dz), L.ptr(ldj), lo, hi, B, x[0].numel(),
                                       L.stream()))
         return out, ldj
@@ -64,6 +69,8 @@ class ActNorm(nn.Module):
             L.check(L.lib().nfb_actnorm_init(L.ptr(z), L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW,
                                              float(self.eps), L.stream()))
             self.initialized = True
+        if G.needs_grad(z, log_df_dz, self.log_scale, self.bias):
+            return G.ActNormFn.apply(z, log_df_dz, self.log_scale, self.bias)
         out = torch.empty_like(z)
         L.check(L.lib().nfb_actnorm_fwd(L.ptr(z), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz),
                                         L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW, L.stream()))
@@ -116,6 +123,8 @@ class BatchNorm(nn.Module):
                 self.running_mean.mul_(1.0 - self.momentum).add_(self.batch_mean * self.momentum)
                 self.running_var.mul_(1.0 - self.momentum).add_(self.batch_var * self.momentum)
         mean, var = self._stats()
+        if G.needs_grad(x, log_det_jacob, self.log_gamma, self.beta):
+            return G.BatchNormFlowFn.apply(x, log_det_jacob, mean, var, self.log_gamma, self.beta)
         out = torch.empty_like(x)
         L.check(L.lib().nfb_bnflow_fwd(L.ptr(x), L.ptr(out), L.ptr(log_det_jacob), L.ptr(log_det_jacob), L.ptr(mean),
                                        L.ptr(var), L.ptr(self.log_gamma.data), L.ptr(self.beta.data), B, C, HW,
@@ -187,6 +196,8 @@ class InvertibleConv1x1(nn.Module):
         return out, log_df_dz
 
     def forward(self, z, log_df_dz):
+        if G.needs_grad(z, log_df_dz, self.L, self.U, self.log_s):
+            return G.InvConv1x1Fn.apply(z, log_df_dz, self.L, self.U, self.log_s, self.P, self.sign_s)
         return self._apply_matrix(z, log_df_dz, self.matrices()[0], 1.0)
 
     def backward(self, y, log_df_dz):
@@ -255,13 +266,16 @@ class Compose(nn.Module):
     def forward(self, z, log_df_dz):
         layers = self.layers
         n, i = len(layers), 0
+        # the fused peepholes are inference kernels; with autograd recording every layer runs through its own Function
+        fuse = self.fuse_steps if not (torch.is_grad_enabled() and (z.requires_grad or log_df_dz.requires_grad or any(
+            p.requires_grad for p in self.parameters()))) else 0
         while i < n:
             layer = layers[i]
             # peepholes (same arithmetic, fewer launches): a whole Glow step ActNorm -> 1x1 conv -> AffineCoupling as one
             # kernel; else an initialised ActNorm followed by the 1x1 convolution as one kernel
             if (i + 1 < n and type(layer) is ActNorm and layer.initialized and type(layers[i + 1]) is InvertibleConv1x1
-                    and self.fuse_steps):
-                if i + 2 < n and self.fuse_steps > 1:
+                    and fuse):
+                if i + 2 < n and fuse > 1:
                     out = _glow_step(layer, layers[i + 1], layers[i + 2], z, log_df_dz)
                     if out is not None:
                         z, log_df_dz = out

@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from . import autograd as G
 
 
 def _dims4(z):
@@ -105,6 +106,8 @@ class Squeeze2d(nn.Module):
         self.odd = odd
 
     def forward(self, z, log_df_dz):
+        if G.needs_grad(z):
+            return G.Squeeze2dFn.apply(z, self.odd, False), log_df_dz
         return squeeze2d_tensor(z, self.odd), log_df_dz
 
     def backward(self, z, log_df_dz):
@@ -121,6 +124,8 @@ class Unsqueeze2d(nn.Module):
         self.odd = odd
 
     def forward(self, z, log_df_dz):
+        if G.needs_grad(z):
+            return G.Squeeze2dFn.apply(z, self.odd, True), log_df_dz
         return unsqueeze2d_tensor(z, self.odd), log_df_dz
 
     def backward(self, z, log_df_dz):

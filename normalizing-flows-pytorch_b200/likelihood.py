@@ -10,6 +10,9 @@ LN2 = math.log(2.0)
 
 def gauss_nll(z, ldj):
     """-> (nll_rows float[B], total double[2] = (sum_b nll_b, B)); nll_b = -(log N(z_b; 0, I) + ldj_b)."""
+    if torch.is_grad_enabled() and (z.requires_grad or ldj.requires_grad):
+        from .flows.autograd import GaussNLLFn
+        return GaussNLLFn.apply(z, ldj)  # differentiable rows (main.py:85: loss = rows.mean())
     z, ldj = L.dev(z, 'z'), L.dev(ldj, 'log_df_dz')
     B = z.size(0)
     rows = torch.empty(B, device=z.device, dtype=torch.float32)

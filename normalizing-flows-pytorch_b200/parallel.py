@@ -92,3 +92,43 @@ def batchnorm_stats_sharded(layer, x_local, group=None):
         layer.running_mean.mul_(1.0 - layer.momentum).add_(layer.batch_mean * layer.momentum)
         layer.running_var.mul_(1.0 - layer.momentum).add_(layer.batch_var * layer.momentum)
     return layer
+
+
+# ---- data-parallel training: one process per GPU, replicated weights, sample-sharded batch ----------
+
+
+def allreduce_gradients(model, group=None, world_size=None):
+    """SUM all-reduce of every parameter gradient as ONE flat bucket (NCCL over NVLink / NVSwitch: a single launch-
+    latency-bound collective instead of one per tensor).  No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    if (world_size or dist.get_world_size(group)) <= 1:
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def train_step(model, optimizer, x_local, group=None):
+    """One optimisation step of main.py:78-92 on this rank's shard of the global batch.
+
+    loss = mean over the GLOBAL batch of -(log N(z; 0, I) + ldj): every rank back-propagates sum(local NLL) / B_global
+    and the gradients are summed across ranks, so the update equals the single-process step on the whole batch whatever
+    the shard sizes.  (Train-mode BatchNorm statistics inside the conditioners stay per-rank, as in plain DDP.)
+    Returns the global mean NLL as a float."""
+    rows, total = model.nll(x_local)
+    total = allreduce_nll(total.clone(), group)
+    loss = rows.sum() / total[1].to(rows.dtype)
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    allreduce_gradients(model, group)
+    optimizer.step()
+    s, n = (float(v) for v in total.tolist())
+    return s / n

@@ -262,7 +262,11 @@ def wn_weight(v, g, eps=1.0e-5):
     return v * (g / (torch.norm(v, dim=0) + eps))
 
 
-def _bn_eval(sd, key, x):
+def _bn_eval(sd, key, x, train=False):
+    """nn.BatchNorm1d/2d inside the conditioners: running statistics (eval) or batch statistics (train mode,
+    modules.py:349-352 under net.train(); functional -- the running buffers are left alone)."""
+    if train:
+        return F.batch_norm(x, None, None, sd[key + '.weight'], sd[key + '.bias'], True, 0.1, 1.0e-5)
     return F.batch_norm(x, sd[key + '.running_mean'], sd[key + '.running_var'], sd[key + '.weight'],
                         sd[key + '.bias'], False, 0.1, 1.0e-5)
 
@@ -275,8 +279,8 @@ def _wn_layer(sd, key, x, pad):
     return F.linear(x, w, b)
 
 
-def resnet_conditioner(sd, prefix, x):
-    """ConvNet.forward / MLP.forward in eval mode (modules.py:391-438, 342-388).
+def resnet_conditioner(sd, prefix, x, train=False):
+    """ConvNet.forward / MLP.forward (modules.py:391-438, 342-388); eval mode unless ``train``.
 
     in_block.0 (weight-normed conv3x3 or linear) -> 2 x [BN, ReLU, WN, BN, ReLU, WN] + skip
     -> BN, ReLU, weight-normed conv1x1 / linear.  The same key layout serves both.
@@ -285,13 +289,13 @@ def resnet_conditioner(sd, prefix, x):
     i = 0
     while (prefix + 'mid_block.%d.net.0.running_mean' % i) in sd:
         p = prefix + 'mid_block.%d.net.' % i
-        y = F.relu(_bn_eval(sd, p + '0', x))
+        y = F.relu(_bn_eval(sd, p + '0', x, train))
         y = _wn_layer(sd, p + '2', y, 1)
-        y = F.relu(_bn_eval(sd, p + '3', y))
+        y = F.relu(_bn_eval(sd, p + '3', y, train))
         y = _wn_layer(sd, p + '5', y, 1)
         x = x + y
         i += 1
-    x = F.relu(_bn_eval(sd, prefix + 'out_block.0', x))
+    x = F.relu(_bn_eval(sd, prefix + 'out_block.0', x, train))
     return _wn_layer(sd, prefix + 'out_block.2', x, 0)
 
 
@@ -519,7 +523,7 @@ def stack_spec(model, dims, datatype, layers, mixtures=4, coupling=None):
     return spec
 
 
-def _coupling(kind, opt, sd, p, z, ldj, inverse):
+def _coupling(kind, opt, sd, p, z, ldj, inverse, train=False):
     d = opt['dims']
     split, merge = split_fn(len(d), opt['masking'], opt['odd'])
     z0, z1 = split(z)
@@ -528,7 +532,7 @@ def _coupling(kind, opt, sd, p, z, ldj, inverse):
         f = mixlog_inverse if inverse else mixlog_transform
         z0, ldj = f(z0, params, ldj, opt['mixtures'], sd[p + 'a_log_scale'], sd[p + 'a_bias'])
     else:
-        params = resnet_conditioner(sd, p + 'net.', z1)
+        params = resnet_conditioner(sd, p + 'net.', z1, train)
         if kind == 'affine':
             z0, ldj = affine_transform(z0, params, ldj, sd[p + 's_log_scale'], sd[p + 's_bias'], inverse)
         else:
@@ -536,7 +540,7 @@ def _coupling(kind, opt, sd, p, z, ldj, inverse):
     return merge(z0, z1), ldj
 
 
-def _apply(kind, opt, sd, p, z, ldj, inverse):
+def _apply(kind, opt, sd, p, z, ldj, inverse, train=False):
     if kind == 'logit':
         return logit_inv(z, ldj) if inverse else logit_fwd(z, ldj, opt['eps'])
     if kind == 'actnorm':
@@ -544,6 +548,10 @@ def _apply(kind, opt, sd, p, z, ldj, inverse):
         return f(z, ldj, sd[p + 'log_scale'], sd[p + 'bias'])
     if kind == 'bnflow':
         f = bnflow_inv if inverse else bnflow_fwd
+        if train and not inverse:  # modules.py:284-296: batch statistics through buffers (.data.copy_): no gradient
+            m, v = bnflow_batch_stats(z.detach())
+            shape = sd[p + 'log_gamma'].shape
+            return f(z, ldj, m.reshape(shape), v.reshape(shape), sd[p + 'log_gamma'], sd[p + 'beta'])
         return f(z, ldj, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'log_gamma'], sd[p + 'beta'])
     if kind == 'invconv':
         f = invconv_inv if inverse else invconv_fwd
@@ -552,15 +560,24 @@ def _apply(kind, opt, sd, p, z, ldj, inverse):
         return (unsqueeze2d_layer(z) if inverse else squeeze2d_layer(z)), ldj
     if kind == 'unsqueeze2d':
         return (squeeze2d_layer(z) if inverse else unsqueeze2d_layer(z)), ldj
-    return _coupling(kind, opt, sd, p, z, ldj, inverse)
+    return _coupling(kind, opt, sd, p, z, ldj, inverse, train)
 
 
-def stack_forward(spec, sd, x):
-    """Model.forward -> Compose.forward (glow.py:62-64, modules.py:331-334); eval mode."""
+def stack_forward(spec, sd, x, train=False):
+    """Model.forward -> Compose.forward (glow.py:62-64, modules.py:331-334); eval mode unless ``train`` (batch
+    statistics in every BatchNorm, as under ``net.train()`` in main.py:71-82).  Differentiable by torch autograd: with
+    leaf tensors in ``sd`` that require grad this is the gradient oracle of the training step."""
     z, ldj = x, torch.zeros(x.shape[0], dtype=x.dtype)
     for i, (kind, opt) in enumerate(spec):
-        z, ldj = _apply(kind, opt, sd, 'net.layers.%d.' % i, z, ldj, False)
+        z, ldj = _apply(kind, opt, sd, 'net.layers.%d.' % i, z, ldj, False, train)
     return z, ldj
+
+
+def mean_nll(z, ldj):
+    """main.py:85: loss = -mean(log N(z; 0, I) + ldj), in the dtype of z (differentiable)."""
+    zf = z.reshape(z.shape[0], -1)
+    logp = -0.5 * (zf * zf).sum(1) - 0.5 * zf.shape[1] * math.log(2.0 * math.pi)
+    return -1.0 * torch.mean(logp + ldj)
 
 
 def stack_backward(spec, sd, z):

@@ -1,0 +1,329 @@
+"""GPU gradient parity (run on the B200 box with ``-m gpu``): the backward kernels of libnfb200 (csrc/backward.cu) through
+the autograd wrappers, against (a) the gradient goldens produced by the reference's own training-mode backward and
+(b) torch CPU autograd through the oracle (fp64) at other shapes.
+
+Tolerances: gradients are compared relative to the largest entry of each tensor -- 2e-4 against the fp32 goldens (the
+conditioner runs on cuDNN here and MKL-DNN there), 2e-5 against the fp64 oracle for the bijection kernels alone.
+"""
+import math
+import types
+
+import pytest
+import torch
+
+from tests import _golden, _gradcheck as GC
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def nfb():
+    import nfb200
+    return nfb200
+
+
+def build_layer(meta):
+    F = nfb().flows
+    kw = dict(meta['kwargs'])
+    for k in ('dims', 'num_features'):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    return getattr(F, meta['kind'])(**kw)
+
+
+def build_model(meta, **extra):
+    n = nfb()
+    cls = {'RealNVP': n.RealNVP, 'Glow': n.Glow, 'Flowpp': n.Flowpp}[meta['kind']]
+    cfg = types.SimpleNamespace(layers=meta['layers'], mixtures=meta.get('mixtures', 4), **extra)
+    return cls(tuple(meta['dims']), meta['datatype'], cfg)
+
+
+def named_grads(module):
+    return {k: p.grad for k, p in module.named_parameters() if p.grad is not None}
+
+
+LAYER_CASES = [n for n in _golden.names('grad_') if not n.startswith('grad_model_')]
+MODEL_CASES = _golden.names('grad_model_')
+
+
+@pytest.mark.parametrize('name', LAYER_CASES)
+def test_layer_gradients_vs_reference_golden(name):
+    meta, a, _ = _golden.load(name)
+    _, src, sd = _golden.load(meta['source'])
+    layer = build_layer(meta)
+    layer.load_state_dict(sd)
+    if hasattr(layer, 'initialized'):
+        layer.initialized = True
+    layer.to(DEV).train()
+    n0 = nfb()._lib.launch_count()
+    x = src['x'].to(DEV).requires_grad_(True)
+    l0 = src['ldj0'].to(DEV).requires_grad_(True)
+    z, l = layer(x, l0)
+    loss = (z * a['Rz'].to(DEV)).sum() + (l * a['Rl'].to(DEV)).sum()
+    loss.backward()
+    assert nfb()._lib.launch_count() - n0 >= 2  # forward + backward kernels of libnfb200 really ran
+    GC.grad_close(z, a['fwd_z'], 2e-5, 'z')
+    GC.grad_close(l, a['fwd_ldj'], 2e-5, 'ldj')
+    GC.grad_close(x.grad, a['gx'], 2e-4, 'gx')
+    GC.grad_close(l0.grad, a['gldj'], 1e-6, 'gldj')
+    got = named_grads(layer)
+    want = {k[5:]: v for k, v in a.items() if k.startswith('grad/')}
+    floor = GC.grad_floor(want)
+    for k, v in want.items():
+        GC.grad_close(got[k], v, 2e-4, k, floor)
+    for k, v in a.items():  # BatchNorm statistics after the step (flow BatchNorm buffers, conditioner running stats)
+        if k.startswith('after/'):
+            GC.grad_close(layer.state_dict()[k[6:]], v, 2e-5, k)
+
+
+@pytest.mark.parametrize('name', MODEL_CASES)
+def test_model_gradients_vs_reference_golden(name):
+    meta, a, _ = _golden.load(name)
+    _, src, sd = _golden.load(meta['source'])
+    net = build_model(meta)
+    net.load_state_dict(sd)
+    net.mark_initialized().to(DEV).train()
+    rows, total = net.nll(src['x'].to(DEV))
+    loss = rows.mean()  # main.py:85
+    loss.backward()
+    assert abs(float(loss) - float(a['loss'])) <= 1e-5 * abs(float(a['loss']))
+    s, cnt = total.tolist()
+    assert abs(s / cnt - float(a['loss'])) <= 1e-5 * abs(float(a['loss']))
+    got = named_grads(net)
+    want = {k[5:]: v for k, v in a.items() if k.startswith('grad/')}
+    assert set(want) <= set(got), sorted(set(want) - set(got))
+    floor = GC.grad_floor(want)
+    for k, v in want.items():
+        GC.grad_close(got[k], v, 5e-4, k, floor)
+    for k, v in a.items():
+        if k.startswith('after/'):
+            GC.grad_close(net.state_dict()[k[6:]], v, 5e-5, k)
+
+
+# ---- bijection kernels alone vs the fp64 oracle: explicit conditioner output, no conditioner network ----------------
+def _geom_opt(dims, masking, odd):
+    return dict(dims=dims, masking=masking, odd=odd, mixtures=4)
+
+
+@pytest.mark.parametrize('dims,masking,B', [((3, 32, 32), 'checkerboard', 8), ((12, 16, 16), 'channelwise', 8),
+                                            ((64, ), 'checkerboard', 512), ((3, 6, 10), 'checkerboard', 3),
+                                            ((6, 5, 3), 'channelwise', 3), ((10, ), 'checkerboard', 7)])
+@pytest.mark.parametrize('odd', [False, True])
+def test_affine_bwd_kernel_vs_oracle_fp64(dims, masking, B, odd):
+    G = nfb().flows.autograd
+    L = nfb()._lib
+    gen = torch.Generator().manual_seed(11)
+    mode = L.SPLIT_1D if len(dims) == 1 else (L.SPLIT_CHECKER if masking == 'checkerboard' else L.SPLIT_CHANNEL)
+    split, merge = O.split_fn(len(dims), masking, odd)
+    z = torch.randn((B, ) + dims, generator=gen)
+    z0, _ = split(z)
+    params = torch.randn((B, 2 * z0.shape[1]) + tuple(z0.shape[2:]), generator=gen)
+    a, b = torch.tensor([0.4]), torch.tensor([-0.1])
+    l0 = torch.randn(B, generator=gen)
+    Rz, Rl = torch.randn(z.shape, generator=gen), torch.randn(B, generator=gen)
+    # oracle (fp64)
+    zd, pd, ad, bd, ld = [t.double().requires_grad_(True) for t in (z, params, a, b, l0)]
+    s0, s1 = split(zd)
+    y0, lo = O.affine_transform(s0, pd, ld, ad, bd)
+    yo = merge(y0, s1)
+    ((yo * Rz.double()).sum() + (lo * Rl.double()).sum()).backward()
+    # kernels
+    zg, pg, ag, bg, lg = [t.to(DEV).requires_grad_(True) for t in (z, params, a, b, l0)]
+    y, l = G.AffineCouplingFn.apply(zg, pg, lg, ag, bg, mode, odd)
+    ((y * Rz.to(DEV)).sum() + (l * Rl.to(DEV)).sum()).backward()
+    GC.grad_close(y, yo, 1e-5, 'y')
+    GC.grad_close(zg.grad, zd.grad, 2e-5, 'gz')
+    GC.grad_close(pg.grad, pd.grad, 2e-5, 'gparams')
+    GC.grad_close(lg.grad, ld.grad, 1e-6, 'gldj')
+    GC.grad_close(ag.grad, ad.grad, 2e-5, 'g s_log_scale')
+    GC.grad_close(bg.grad, bd.grad, 2e-5, 'g s_bias')
+
+
+@pytest.mark.parametrize('dims,masking,K,B', [((3, 16, 16), 'checkerboard', 8, 4), ((12, 8, 8), 'channelwise', 4, 4),
+                                              ((6, ), 'checkerboard', 5, 9)])
+@pytest.mark.parametrize('odd', [False, True])
+def test_mixlog_bwd_kernel_vs_oracle_fp64(dims, masking, K, B, odd):
+    G = nfb().flows.autograd
+    L = nfb()._lib
+    gen = torch.Generator().manual_seed(12)
+    mode = L.SPLIT_1D if len(dims) == 1 else (L.SPLIT_CHECKER if masking == 'checkerboard' else L.SPLIT_CHANNEL)
+    split, merge = O.split_fn(len(dims), masking, odd)
+    z = torch.randn((B, ) + dims, generator=gen)
+    z0, _ = split(z)
+    params = torch.randn((B, (2 + 3 * K) * z0.shape[1]) + tuple(z0.shape[2:]), generator=gen)
+    a, b = torch.tensor([0.3]), torch.tensor([0.05])
+    l0 = torch.randn(B, generator=gen)
+    Rz, Rl = torch.randn(z.shape, generator=gen), torch.randn(B, generator=gen)
+    zd, pd, ad, bd, ld = [t.double().requires_grad_(True) for t in (z, params, a, b, l0)]
+    s0, s1 = split(zd)
+    y0, lo = O.mixlog_transform(s0, pd, ld, K, ad, bd)
+    yo = merge(y0, s1)
+    ((yo * Rz.double()).sum() + (lo * Rl.double()).sum()).backward()
+    zg, pg, ag, bg, lg = [t.to(DEV).requires_grad_(True) for t in (z, params, a, b, l0)]
+    y, l = G.MixLogCouplingFn.apply(zg, pg, lg, ag, bg, mode, odd, K)
+    ((y * Rz.to(DEV)).sum() + (l * Rl.to(DEV)).sum()).backward()
+    GC.grad_close(y, yo, 2e-5, 'y')
+    GC.grad_close(zg.grad, zd.grad, 5e-5, 'gz')
+    GC.grad_close(pg.grad, pd.grad, 5e-5, 'gparams')
+    GC.grad_close(ag.grad, ad.grad, 5e-5, 'g a_log_scale')
+    GC.grad_close(bg.grad, bd.grad, 5e-5, 'g a_bias')
+
+
+@pytest.mark.parametrize('dims,masking,K,B', [((64, ), 'checkerboard', 8, 256), ((4, 8, 8), 'checkerboard', 8, 4),
+                                              ((4, 8, 8), 'channelwise', 5, 4)])
+@pytest.mark.parametrize('odd', [False, True])
+def test_rqs_bwd_kernel_vs_oracle_fp64(dims, masking, K, B, odd):
+    G = nfb().flows.autograd
+    L = nfb()._lib
+    gen = torch.Generator().manual_seed(13)
+    mode = L.SPLIT_1D if len(dims) == 1 else (L.SPLIT_CHECKER if masking == 'checkerboard' else L.SPLIT_CHANNEL)
+    split, merge = O.split_fn(len(dims), masking, odd)
+    z = torch.randn((B, ) + dims, generator=gen) * 2.0  # some mass in the identity tails
+    z0, _ = split(z)
+    params = torch.randn((B, (3 * K - 1) * z0.shape[1]) + tuple(z0.shape[2:]), generator=gen)
+    l0 = torch.randn(B, generator=gen)
+    Rz, Rl = torch.randn(z.shape, generator=gen), torch.randn(B, generator=gen)
+    zd, pd, ld = [t.double().requires_grad_(True) for t in (z, params, l0)]
+    s0, s1 = split(zd)
+    y0, lo = O.rqs_transform(s0, pd, ld, K, 3.0)
+    yo = merge(y0, s1)
+    ((yo * Rz.double()).sum() + (lo * Rl.double()).sum()).backward()
+    zg, pg, lg = [t.to(DEV).requires_grad_(True) for t in (z, params, l0)]
+    y, l = G.RQSCouplingFn.apply(zg, pg, lg, mode, odd, K, 3.0)
+    ((y * Rz.to(DEV)).sum() + (l * Rl.to(DEV)).sum()).backward()
+    GC.grad_close(y, yo, 2e-5, 'y')
+    GC.grad_close(zg.grad, zd.grad, 1e-4, 'gz')
+    GC.grad_close(pg.grad, pd.grad, 1e-4, 'gparams')
+
+
+@pytest.mark.parametrize('shape', [(8, 48, 8, 8), (4, 192, 8, 8), (16, 3, 32, 32), (5, 7, 3, 5), (33, 6)])
+def test_channel_layers_and_invconv_bwd_vs_oracle_fp64(shape):
+    """ActNorm, flow BatchNorm (train mode), InvertibleConv1x1, Logit, Squeeze2d at the BASELINE channel counts and odd shapes."""
+    F = nfb().flows
+    gen = torch.Generator().manual_seed(14)
+    B, C = shape[0], shape[1]
+    dims = tuple(shape[1:])
+    x = torch.randn(shape, generator=gen)
+    l0 = torch.randn(B, generator=gen)
+    Rz, Rl = torch.randn(shape, generator=gen), torch.randn(B, generator=gen)
+    pshape = [1, C] + [1] * (len(shape) - 2)
+
+    def run_gpu(layer, xin):
+        layer.to(DEV)
+        xg, lg = xin.to(DEV).requires_grad_(True), l0.to(DEV).requires_grad_(True)
+        z, l = layer(xg, lg)
+        ((z * Rz.to(DEV)).sum() + (l * Rl.to(DEV)).sum()).backward()
+        return z, xg.grad, lg.grad, {k: p.grad for k, p in layer.named_parameters() if p.grad is not None}
+
+    def run_oracle(fn, xin, sd):
+        leaves = GC.leaf_state(sd, torch.float64)
+        xd, ld = xin.double().requires_grad_(True), l0.double().requires_grad_(True)
+        z, l = fn(xd, ld, leaves)
+        ((z * Rz.double()).sum() + (l * Rl.double()).sum()).backward()
+        return z, xd.grad, ld.grad, {k: t.grad for k, t in leaves.items() if t.requires_grad and t.grad is not None}
+
+    def compare(g, o, tol, what):
+        GC.grad_close(g[0], o[0], tol, what + ' out')
+        GC.grad_close(g[1], o[1], tol, what + ' gx')
+        GC.grad_close(g[2], o[2], 1e-6, what + ' gldj')
+        for k, v in o[3].items():
+            GC.grad_close(g[3][k], v, tol, what + ' ' + k)
+
+    # ActNorm
+    an = F.ActNorm(dims)
+    with torch.no_grad():
+        an.log_scale.copy_(0.3 * torch.randn(pshape, generator=gen))
+        an.bias.copy_(torch.randn(pshape, generator=gen))
+    an.initialized = True
+    sd = {k: v.clone() for k, v in an.state_dict().items()}
+    compare(run_gpu(an, x), run_oracle(lambda a, l, s: O.actnorm_fwd(a, l, s['log_scale'], s['bias']), x, sd), 2e-5, 'actnorm')
+    # flow BatchNorm, train mode, affine
+    bn = F.BatchNorm(dims, affine=True)
+    with torch.no_grad():
+        bn.log_gamma.copy_(0.2 * torch.randn(pshape, generator=gen))
+        bn.beta.copy_(torch.randn(pshape, generator=gen))
+    bn.train()
+    sd = {k: v.clone() for k, v in bn.state_dict().items()}
+
+    def bn_oracle(a, l, s):
+        m, v = O.bnflow_batch_stats(a.detach())
+        return O.bnflow_fwd(a, l, m.reshape(pshape), v.reshape(pshape), s['log_gamma'], s['beta'])
+
+    compare(run_gpu(bn, x), run_oracle(bn_oracle, x, sd), 2e-5, 'bnflow')
+    # InvertibleConv1x1
+    torch.manual_seed(3)
+    cv = F.InvertibleConv1x1(C)
+    with torch.no_grad():
+        cv.L.add_(0.05 / math.sqrt(C) * torch.randn(C, C, generator=gen))
+        cv.U.add_(0.05 / math.sqrt(C) * torch.randn(C, C, generator=gen))
+        cv.log_s.add_(0.1 * torch.randn(C, generator=gen))
+    sd = {k: v.clone() for k, v in cv.state_dict().items()}
+    compare(run_gpu(cv, x),
+            run_oracle(lambda a, l, s: O.invconv_fwd(a, l, s['P'], s['L'], s['U'], s['log_s'], s['sign_s']), x, sd), 5e-5,
+            'invconv')
+    # Logit (input in (0,1), some of it outside the clamp range)
+    u = torch.rand(shape, generator=gen)
+    lg = F.Logit(eps=0.01)
+    compare(run_gpu(lg, u), run_oracle(lambda a, l, s: O.logit_fwd(a, l, 0.01), u, {}), 2e-5, 'logit')
+    # Squeeze2d: gradient is the inverse permutation, bit exact
+    if len(shape) == 4 and shape[2] % 2 == 0 and shape[3] % 2 == 0:
+        xg = x.to(DEV).requires_grad_(True)
+        z, _ = F.Squeeze2d()(xg, None)
+        R = torch.randn(z.shape, generator=gen)
+        (z * R.to(DEV)).sum().backward()
+        assert torch.equal(xg.grad.cpu(), O.unsqueeze2d_layer(R))
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(kind='Glow', dims=(3, 32, 32), datatype='image', layers=2, B=8),
+    dict(kind='RealNVP', dims=(64, ), datatype=None, layers=4, B=256, coupling='rqs'),   # BASELINE cfg 4 bijection
+    dict(kind='RealNVP', dims=(2, ), datatype=None, layers=6, B=512),
+    dict(kind='Flowpp', dims=(3, 16, 16), datatype='image', layers=1, B=4, mixtures=4),
+])
+def test_training_step_gradients_vs_oracle(cfg):
+    """Whole training step (train mode, loss of main.py:85) against CPU autograd through the oracle in fp32."""
+    torch.manual_seed(0)
+    extra = {'coupling': cfg['coupling']} if 'coupling' in cfg else {}
+    meta = dict(kind=cfg['kind'], dims=list(cfg['dims']), datatype=cfg['datatype'], layers=cfg['layers'],
+                mixtures=cfg.get('mixtures', 4))
+    net = build_model(meta, **extra)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand((cfg['B'], ) + cfg['dims'], generator=gen) if cfg['datatype'] == 'image' else \
+        torch.randn((cfg['B'], ) + cfg['dims'], generator=gen)
+    net.to(DEV).train()
+    with torch.no_grad():
+        net(x.to(DEV))  # ActNorm data-dependent init (modules.py:238-244) on the device
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    rows, _ = net.nll(x.to(DEV))
+    loss = rows.mean()
+    loss.backward()
+    lo, go = GC.oracle_model_grads(meta, sd, x, torch.float32, True, cfg.get('coupling'))
+    assert abs(float(loss) - float(lo)) <= 2e-5 * abs(float(lo))
+    got = named_grads(net)
+    buffers = dict(net.named_buffers())
+    floor = GC.grad_floor(go)
+    for k, v in go.items():
+        if k in buffers:  # e.g. log_gamma / beta of BatchNorm(affine=False): buffers, not trained (modules.py:269-273)
+            continue
+        GC.grad_close(got[k], v, 1e-3, k, floor)
+
+
+def test_training_reduces_loss_and_matches_eval_path():
+    """A few Adam steps through nfb200.parallel.train_step lower the NLL; afterwards the inference path (fused kernels,
+    packed weights rebuilt from the updated parameters) agrees with the autograd path in eval mode."""
+    n = nfb()
+    torch.manual_seed(0)
+    net = n.Glow((3, 16, 16), 'image', types.SimpleNamespace(layers=2, mixtures=4)).to(DEV)
+    x = torch.rand(32, 3, 16, 16, generator=torch.Generator().manual_seed(5)).to(DEV)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    losses = [n.parallel.train_step(net, opt, x) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
+    net.eval()
+    with torch.no_grad():
+        z0, l0 = net(x)
+    z1, l1 = net(x)  # autograd path (parameters require grad), eval-mode statistics
+    assert z1.requires_grad and not z0.requires_grad
+    GC.grad_close(z1, z0, 2e-5, 'autograd vs inference z')
+    GC.grad_close(l1, l0, 2e-5, 'autograd vs inference ldj')

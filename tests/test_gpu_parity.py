@@ -19,6 +19,13 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(autouse=True)
+def _inference_path():
+    """These tests cover the inference kernels (in-place log-det, fused peepholes); gradients are tests/test_gpu_backward.py."""
+    with torch.no_grad():
+        yield
+
+
 def nfb():
     import nfb200
     return nfb200
@@ -93,7 +100,7 @@ def build_layer(meta):
     return layer
 
 
-LAYER_CASES = [n for n in _golden.names() if not n.startswith(('model_', 'permutations', 'stats_'))]
+LAYER_CASES = [n for n in _golden.names() if not n.startswith(('model_', 'permutations', 'stats_', 'grad_'))]
 
 
 @pytest.mark.parametrize('name', LAYER_CASES)
