@@ -298,27 +298,47 @@ def dominant_kernel_probe(net, batch, clocks):
 
 def train_probe(net, dev_ring, batch, world, steps):
     """Training step of main.py:78-92 on the new path: train-mode forward (bijection kernels + cuDNN/cuBLAS conditioner),
-    loss = global mean NLL, backward through csrc/backward.cu, flat-bucket gradient all-reduce, Adam.  Eager (no graph);
-    runs on a deep copy so the benchmarked weights are untouched.  Informational: the headline metric is fwd+logdet."""
+    loss = global mean NLL, backward through csrc/backward.cu, flat-bucket gradient all-reduce, Adam -- replayed as CUDA
+    graphs (nfb200.parallel.GraphedTrainStep); the eager step is timed next to it.  Runs on deep copies so the
+    benchmarked weights are untouched.  Informational: the headline metric is fwd+logdet."""
     import copy
     import nfb200
     from nfb200 import parallel
+    out = {'unit': 'samples/s',
+           'note': 'train-mode fwd + gradient kernels + flat-bucket all-reduce + Adam; conditioner fwd/bwd on cuDNN'}
+    ring = len(dev_ring)
+    # eager
     tnet = copy.deepcopy(net).train()
     opt = torch.optim.Adam(tnet.parameters(), lr=1e-4)
-    losses = [parallel.train_step(tnet, opt, dev_ring[i % len(dev_ring)]) for i in range(2)]
+    losses = [parallel.train_step(tnet, opt, dev_ring[i % ring]) for i in range(2)]
     torch.cuda.synchronize()
     n0 = nfb200._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    for i in range(2):
+        losses.append(parallel.train_step(tnet, opt, dev_ring[(2 + i) % ring]))
+    e1.record()
+    torch.cuda.synchronize()
+    out['eager'] = {'value': batch * world / (e0.elapsed_time(e1) / 2 * 1e-3), 'ms_per_step': e0.elapsed_time(e1) / 2,
+                    'loss_first': losses[0], 'loss_last': losses[-1]}
+    out['nfb200_launches_per_step'] = (nfb200._lib.launch_count() - n0) // 2
+    del tnet, opt
+    # graph replay
+    gnet = copy.deepcopy(net).train()
+    gopt = torch.optim.Adam(gnet.parameters(), lr=1e-4, capturable=True)
+    step = parallel.GraphedTrainStep(gnet, gopt, dev_ring[0])
+    first = float(step(dev_ring[0]))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for i in range(steps):
-        losses.append(parallel.train_step(tnet, opt, dev_ring[(2 + i) % len(dev_ring)]))
+        loss = step(dev_ring[(1 + i) % ring])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {'value': batch * world / (ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms,
-            'nfb200_launches_per_step': (nfb200._lib.launch_count() - n0) // steps, 'loss_first': losses[0],
-            'loss_last': losses[-1],
-            'note': 'train-mode fwd + backward kernels + gradient all-reduce + Adam, eager; conditioner fwd/bwd on cuDNN'}
+    out.update({'value': batch * world / (ms * 1e-3), 'ms_per_step': ms, 'mode': 'cuda-graph replay',
+                'loss_first': first, 'loss_last': float(loss)})
+    return out
 
 
 def load_peaks():

@@ -66,6 +66,13 @@ _SIGNATURES = {
     'nfb_invconv1x1_weight_bwd': [_P] * 10 + [_I, _I, _I, _P],
     'nfb_logit_bwd': [_P, _P, _P, _P, _F, _F, _I, _I, _P],
     'nfb_gauss_nll_bwd': [_P, _P, _P, _P, _I, _I, _P],
+    'nfb_wn_pack_train': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'nfb_wn_bwd': [_P, _P, _P, _P, _P, _I, _I, _F, _P],
+    'nfb_conv_train': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_conv_train_wgrad': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_bn_relu_fwd': [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P],
+    'nfb_bn_relu_bwd_reduce': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 _RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong}
 

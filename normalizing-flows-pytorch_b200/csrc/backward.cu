@@ -94,11 +94,144 @@ inline int flat_grid(long long work) {
     return static_cast<int>(blocks);
 }
 
+// ---- vectorised variant: the forward kernel's item decomposition (coupling_affine.cu) -- 8 consecutive floats of z in its
+// original layout per item, every access a 16-byte load/store, checkerboard classification warp-uniform (no integer
+// division per element).  One warp per sample, lanes stride over the items.
+struct Bwd4 {
+    float4 gz, gr;
+};
+__device__ __forceinline__ Bwd4 affine_bwd4(float z0, float z1, float z2, float z3, float g0, float g1, float g2, float g3,
+                                            const float4& sr, float glv, float a, float b, float& acc_a, float& acc_b) {
+    Bwd4 o;
+    const float zz[4] = {z0, z1, z2, z3}, gg[4] = {g0, g1, g2, g3}, ss[4] = {sr.x, sr.y, sr.z, sr.w};
+    float gzv[4], grv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float th = tanhf(ss[i]);
+        const float es = expf(__fadd_rn(__fmul_rn(th, a), b));
+        gzv[i] = gg[i] * es;
+        const float gs = fmaf(gg[i] * zz[i], es, glv);
+        grv[i] = gs * a * (1.f - th * th);
+        acc_a = fmaf(gs, th, acc_a);
+        acc_b += gs;
+    }
+    o.gz = make_float4(gzv[0], gzv[1], gzv[2], gzv[3]);
+    o.gr = make_float4(grv[0], grv[1], grv[2], grv[3]);
+    return o;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) affine_bwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ params,
+                                                            const float* __restrict__ gy, const float* __restrict__ gl,
+                                                            float* __restrict__ gz, float* __restrict__ gparams,
+                                                            double* __restrict__ gab, const float* __restrict__ pa,
+                                                            const float* __restrict__ pb, SplitGeom g, int items,
+                                                            int sh_ipl, int sh_wq) {
+    __shared__ double red[33];
+    const float a = __ldg(pa), b = __ldg(pb);
+    float acc_a = 0.f, acc_b = 0.f;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < g.B; row += gridDim.x * wpb) {
+        const size_t base = static_cast<size_t>(row) * g.D;
+        const float* zr = z + base;
+        const float* gyr = gy + base;
+        const float* pr = params + base;
+        float* gzr = gz + base;
+        float* gpr = gparams + base;
+        const float glv = gl ? __ldg(gl + row) : 0.f;
+        for (int it = lane; it < items; it += 32) {
+            if (MODE == NFB_SPLIT_CHANNEL) {
+                const int o0 = (g.odd ? g.n0 : 0) + 8 * it, o1 = (g.odd ? 0 : g.n0) + 8 * it;
+                const float4 v0 = ldg4(zr + o0), v1 = ldg4(zr + o0 + 4), q0 = ldg4(gyr + o0), q1 = ldg4(gyr + o0 + 4);
+                const float4 s0 = ldg4(pr + g.n0 + 8 * it), s1 = ldg4(pr + g.n0 + 8 * it + 4);
+                st4(gzr + o1, ldg4(gyr + o1));
+                st4(gzr + o1 + 4, ldg4(gyr + o1 + 4));
+                const Bwd4 r0 = affine_bwd4(v0.x, v0.y, v0.z, v0.w, q0.x, q0.y, q0.z, q0.w, s0, glv, a, b, acc_a, acc_b);
+                const Bwd4 r1 = affine_bwd4(v1.x, v1.y, v1.z, v1.w, q1.x, q1.y, q1.z, q1.w, s1, glv, a, b, acc_a, acc_b);
+                st4(gzr + o0, r0.gz); st4(gzr + o0 + 4, r1.gz);
+                st4(gpr + 8 * it, q0); st4(gpr + 8 * it + 4, q1);
+                st4(gpr + g.n0 + 8 * it, r0.gr); st4(gpr + g.n0 + 8 * it + 4, r1.gr);
+            } else if (MODE == NFB_SPLIT_1D) {
+                const float4 v0 = ldg4(zr + 8 * it), v1 = ldg4(zr + 8 * it + 4);
+                float4 q0 = ldg4(gyr + 8 * it), q1 = ldg4(gyr + 8 * it + 4);
+                const float4 sr = ldg4(pr + g.n0 + 4 * it);
+                if (!g.odd) {
+                    const Bwd4 r = affine_bwd4(v0.x, v0.z, v1.x, v1.z, q0.x, q0.z, q1.x, q1.z, sr, glv, a, b, acc_a, acc_b);
+                    st4(gpr + 4 * it, make_float4(q0.x, q0.z, q1.x, q1.z));
+                    q0.x = r.gz.x; q0.z = r.gz.y; q1.x = r.gz.z; q1.z = r.gz.w;
+                    st4(gpr + g.n0 + 4 * it, r.gr);
+                } else {
+                    const Bwd4 r = affine_bwd4(v0.y, v0.w, v1.y, v1.w, q0.y, q0.w, q1.y, q1.w, sr, glv, a, b, acc_a, acc_b);
+                    st4(gpr + 4 * it, make_float4(q0.y, q0.w, q1.y, q1.w));
+                    q0.y = r.gz.x; q0.w = r.gz.y; q1.y = r.gz.z; q1.w = r.gz.w;
+                    st4(gpr + g.n0 + 4 * it, r.gr);
+                }
+                st4(gzr + 8 * it, q0); st4(gzr + 8 * it + 4, q1);
+            } else {
+                // items ordered (c, dy, i, jb) as in the forward kernel: all items of one (c, dy) share the two squeezed
+                // channels k (even x) and k+1 (odd x)
+                const int wq = g.w >> 2, ipl = g.h * wq;
+                int cd, rem, i, jb;
+                if (sh_ipl >= 0) { cd = it >> sh_ipl; rem = it & (ipl - 1); i = rem >> sh_wq; jb = rem & (wq - 1); }
+                else { cd = it / ipl; rem = it - cd * ipl; i = rem / wq; jb = rem - i * wq; }
+                const int k = 2 * cd;
+                const int e0 = (cd >> 1) * g.HW + (2 * i + (cd & 1)) * g.W + 8 * jb;
+                const int qe = (k >= g.C) + (k >= 2 * g.C) + (k >= 3 * g.C);
+                const int qo = (k + 1 >= g.C) + (k + 1 >= 2 * g.C) + (k + 1 >= 3 * g.C);
+                const bool te = ((qe == 0 || qe == 3) ? 1 : 0) != g.odd, to = ((qo == 0 || qo == 3) ? 1 : 0) != g.odd;
+                const int me = (qe == 0) ? k : (qe == 3) ? k - 2 * g.C : k - g.C;
+                const int mo = (qo == 0) ? k + 1 : (qo == 3) ? k + 1 - 2 * g.C : k + 1 - g.C;
+                const int hw = g.h * g.w, sp = i * g.w + 4 * jb;
+                float4 q0 = ldg4(gyr + e0), q1 = ldg4(gyr + e0 + 4);
+                float4 v0, v1;
+                if (te || to) { v0 = ldg4(zr + e0); v1 = ldg4(zr + e0 + 4); }
+                if (te) {
+                    const float4 sr = ldg4(pr + g.n0 + me * hw + sp);
+                    const Bwd4 r = affine_bwd4(v0.x, v0.z, v1.x, v1.z, q0.x, q0.z, q1.x, q1.z, sr, glv, a, b, acc_a, acc_b);
+                    st4(gpr + me * hw + sp, make_float4(q0.x, q0.z, q1.x, q1.z));
+                    st4(gpr + g.n0 + me * hw + sp, r.gr);
+                    q0.x = r.gz.x; q0.z = r.gz.y; q1.x = r.gz.z; q1.z = r.gz.w;
+                }
+                if (to) {
+                    const float4 sr = ldg4(pr + g.n0 + mo * hw + sp);
+                    const Bwd4 r = affine_bwd4(v0.y, v0.w, v1.y, v1.w, q0.y, q0.w, q1.y, q1.w, sr, glv, a, b, acc_a, acc_b);
+                    st4(gpr + mo * hw + sp, make_float4(q0.y, q0.w, q1.y, q1.w));
+                    st4(gpr + g.n0 + mo * hw + sp, r.gr);
+                    q0.y = r.gz.x; q0.w = r.gz.y; q1.y = r.gz.z; q1.w = r.gz.w;
+                }
+                st4(gzr + e0, q0); st4(gzr + e0 + 4, q1);
+            }
+        }
+    }
+    const double sa = block_sum_d(acc_a, red), sb = block_sum_d(acc_b, red);
+    if (threadIdx.x == 0) { atomicAdd(gab, sa); atomicAdd(gab + 1, sb); }
+}
+
 template <int MODE>
 static int launch_affine_bwd(const float* z, const float* params, const float* gy, const float* gl, float* gz,
                              float* gparams, double* gab, const float* a, const float* b, const SplitGeom& g,
                              cudaStream_t st) {
     const long long total = static_cast<long long>(g.B) * g.D;
+    const bool al = aligned16(z) && aligned16(gy) && aligned16(gz) && aligned16(params) && aligned16(gparams);
+    int items = 0;
+    bool vec8 = al;
+    if (MODE == NFB_SPLIT_CHANNEL) { vec8 = vec8 && (g.n0 % 8 == 0); items = g.n0 / 8; }
+    else if (MODE == NFB_SPLIT_1D) { vec8 = vec8 && (g.D % 8 == 0); items = g.D / 8; }
+    else                           { vec8 = vec8 && (g.W % 8 == 0); items = g.D / 8; }
+    if (vec8 && items >= 32) {
+        int sh_ipl = -1, sh_wq = 0;
+        if (MODE == NFB_SPLIT_CHECKER) {
+            const int wq = g.w / 4, ipl = g.h * wq;
+            auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+            auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+            if (is_pow2(wq) && is_pow2(ipl)) { sh_ipl = lg(ipl); sh_wq = lg(wq); }
+        }
+        long long grid = (static_cast<long long>(g.B) + 7) / 8;
+        if (grid > kSMs * 16) grid = kSMs * 16;
+        affine_bwd_vec_kernel<MODE><<<static_cast<int>(grid), 256, 0, st>>>(z, params, gy, gl, gz, gparams, gab, a, b, g,
+                                                                          items, sh_ipl, sh_wq);
+        return launch_status();
+    }
     const bool vec = (g.D % 4 == 0) && aligned16(z) && aligned16(gy) && aligned16(gz);
     if (vec) affine_bwd_kernel<MODE, true><<<flat_grid(total / 4), 256, 0, st>>>(z, params, gy, gl, gz, gparams, gab, a, b, g);
     else affine_bwd_kernel<MODE, false><<<flat_grid(total), 256, 0, st>>>(z, params, gy, gl, gz, gparams, gab, a, b, g);

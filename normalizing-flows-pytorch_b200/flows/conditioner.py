@@ -2,8 +2,9 @@
 
 ``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
 -> out_block (BN, ReLU, WN-layer).  Eval mode without autograd: ONE fused kernel over folded weights.  Train mode (batch
-statistics, modules.py:349-352) or with gradients recorded: the same network as cuDNN / cuBLAS ops under torch autograd
-(``_forward_autograd``) -- a native train-mode conditioner is the next step of SURVEY.md 8f.
+statistics, modules.py:349-352): ``ConvNet`` at 16x16 / 8x8 / 4x4 runs layer by layer on libnfb200 kernels, forward and
+backward (``conditioner_train.py``); ``MLP``, other spatial sizes and eval-mode-with-gradients use cuDNN / cuBLAS ops under
+torch autograd (``_forward_autograd``).
 """
 import ctypes
 
@@ -167,8 +168,33 @@ class _ResNetConditioner(nn.Module):
             return F.conv2d(x, w, wn.module.bias, 1, (w.size(2) - 1) // 2)
         return F.linear(x, w, wn.module.bias)
 
+    # train mode on libnfb200 kernels (ConvNet at 16x16 / 8x8 / 4x4); False = cuDNN / cuBLAS ops under torch autograd
+    native_train = True
+
+    def _forward_native_train(self, x):
+        from .conditioner_train import SUPPORTED_HW, ConvNetTrainFn
+        if not (self.conv and self.training and self.native_train and x.dim() == 4 and len(self.mid_block) == 2
+                and self.base_filters == 32 and tuple(x.shape[2:]) in SUPPORTED_HW):
+            return None
+        wn = [self.in_block[0]] + [blk.net[i] for blk in self.mid_block for i in (2, 5)] + [self.out_block[2]]
+        bn = [blk.net[i] for blk in self.mid_block for i in (0, 3)] + [self.out_block[0]]
+        ts = []
+        for m in wn:
+            ts += [m.module.weight_v, m.module.weight_g, m.module.bias]
+        for m in bn:
+            ts += [m.weight, m.bias]
+        for m in bn:
+            ts += [m.running_mean, m.running_var]
+        out = ConvNetTrainFn.apply(x, (wn[0].eps, bn[0].eps, bn[0].momentum), *ts)
+        for m in bn:
+            m.num_batches_tracked += 1  # nn.BatchNorm bookkeeping (momentum is fixed, so it does not enter the update)
+        return out
+
     def _forward_autograd(self, x):
         x = L.dev(x, 'conditioner input')
+        out = self._forward_native_train(x)
+        if out is not None:
+            return out
         x = self._wn_apply(self.in_block[0], x)
         for blk in self.mid_block:
             y = F.relu(blk.net[0](x))

@@ -1,0 +1,143 @@
+"""Train-mode ``ConvNet`` conditioner (modules.py:416-438 under ``net.train()``) on libnfb200 kernels, forward and backward.
+
+In train mode the conditioner's BatchNorm layers use batch statistics, so the one-kernel eval conditioner does not apply:
+the network runs layer by layer (``csrc/conditioner_train.cu``) -- WeightNorm + packing, convolution (+ bias, + residual,
++ channel moments), BatchNorm+ReLU -- and the backward pass mirrors it (weight gradient, data gradient = the same
+convolution kernel over flipped / transposed packed weights, BatchNorm+ReLU backward in two passes).  Every intermediate
+activation is kept for the backward pass (11 tensors of (B, 32, h, w) per conditioner call).
+
+``ConvNetTrainFn.apply(x, cfg, *tensors)`` with ``tensors`` =
+  6 x (weight_v, weight_g, bias)   of in_block.0, mid_block.{0,1}.net.{2,5}, out_block.2          (differentiable)
+  5 x (weight, bias)               of mid_block.{0,1}.net.{0,3}, out_block.0 (BatchNorm gamma / beta) (differentiable)
+  5 x (running_mean, running_var)  of the same BatchNorms                                      (updated in place)
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _lib as L
+
+SUPPORTED_HW = ((16, 16), (8, 8), (4, 4))
+F32 = 32  # base_filters
+
+
+def _conv(x, w_packed, bias, skip, cin, cout, ks, want_stats):
+    B, _, h, w = x.shape
+    out = torch.empty((B, cout, h, w), device=x.device, dtype=torch.float32)
+    stats = torch.empty(2 * cout, device=x.device, dtype=torch.float64) if want_stats else None
+    L.check(L.lib().nfb_conv_train(L.ptr(x), L.ptr(w_packed), L.ptr(bias) if bias is not None else None,
+                                   L.ptr(skip) if skip is not None else None, L.ptr(out),
+                                   stats.data_ptr() if want_stats else None, B, cin, cout, h, w, ks, L.stream()))
+    return out, stats
+
+
+def _bn_relu(x, stats, gamma, beta, rmean, rvar, momentum, eps):
+    B, C, h, w = x.shape
+    a = torch.empty_like(x)
+    mr = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+    L.check(L.lib().nfb_bn_relu_fwd(L.ptr(x), stats.data_ptr(), L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar),
+                                    float(momentum), float(eps), L.ptr(a), L.ptr(mr), B, C, h * w, L.stream()))
+    return a, mr
+
+
+def _wgrad(gy, a, cin, cout, ks):
+    B, _, h, w = gy.shape
+    gw = torch.empty((cout, cin, ks, ks), device=gy.device, dtype=torch.float32)
+    gb = torch.empty(cout, device=gy.device, dtype=torch.float32)
+    L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), B, cin, cout, h, w, ks, L.stream()))
+    return gw, gb
+
+
+def _bn_relu_bwd(ga, a, x, mr, gamma, add):
+    """-> (gx, g_gamma, g_beta): ReLU mask, the two batch sums, then the BatchNorm input gradient (+ residual branch)."""
+    B, C, h, w = x.shape
+    U = torch.empty_like(x)
+    sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    L.check(L.lib().nfb_bn_relu_bwd_reduce(L.ptr(ga), L.ptr(a), L.ptr(x), L.ptr(mr), L.ptr(U), sums.data_ptr(), B, C, h * w,
+                                           L.stream()))
+    gx = torch.empty_like(x)
+    gg, gb = torch.empty_like(gamma), torch.empty_like(gamma)
+    L.check(L.lib().nfb_bn_bwd_apply(L.ptr(U), L.ptr(x), L.ptr(mr), L.ptr(gamma), sums.data_ptr(),
+                                     L.ptr(add) if add is not None else None, L.ptr(gx), L.ptr(gg), L.ptr(gb), B, C, h * w,
+                                     L.stream()))
+    return gx, gg, gb
+
+
+class ConvNetTrainFn(Function):
+
+    @staticmethod
+    def forward(ctx, x, cfg, *T):
+        x = L.dev(x, 'conditioner input')
+        wn, bn, rs = T[:18], T[18:28], T[28:38]
+        wn_eps, bn_eps, momentum = cfg
+        cin, cout = wn[0].size(1), wn[15].size(0)
+        packed = []
+        for i in range(6):
+            v, g = wn[3 * i], wn[3 * i + 1]
+            O, I, KK = v.size(0), v.size(1), v[0, 0].numel()
+            n = ((O + 31) // 32) * ((I + 31) // 32) * 32 * KK * 32
+            w_nat = torch.empty_like(v)
+            w_fwd = torch.zeros(n, device=v.device, dtype=torch.float32)
+            w_bwd = torch.zeros(n, device=v.device, dtype=torch.float32)
+            L.check(L.lib().nfb_wn_pack_train(L.ptr(v), L.ptr(g), L.ptr(w_nat), L.ptr(w_fwd), L.ptr(w_bwd), O, I, KK,
+                                              float(wn_eps), L.stream()))
+            packed.append((w_fwd, w_bwd))
+        b = [wn[3 * i + 2] for i in range(6)]
+        gam, bet = [bn[2 * i] for i in range(5)], [bn[2 * i + 1] for i in range(5)]
+
+        def bnr(t, st, i):
+            return _bn_relu(t, st, gam[i], bet[i], rs[2 * i], rs[2 * i + 1], momentum, bn_eps)
+
+        h0, st = _conv(x, packed[0][0], b[0], None, cin, F32, 3, True)
+        a1, mr1 = bnr(h0, st, 0)
+        y1, st = _conv(a1, packed[1][0], b[1], None, F32, F32, 3, True)
+        a2, mr2 = bnr(y1, st, 1)
+        h1, st = _conv(a2, packed[2][0], b[2], h0, F32, F32, 3, True)
+        a3, mr3 = bnr(h1, st, 2)
+        y2, st = _conv(a3, packed[3][0], b[3], None, F32, F32, 3, True)
+        a4, mr4 = bnr(y2, st, 3)
+        h2, st = _conv(a4, packed[4][0], b[4], h1, F32, F32, 3, True)
+        a5, mr5 = bnr(h2, st, 4)
+        out, _ = _conv(a5, packed[5][0], b[5], None, F32, cout, 1, False)
+        ctx.save_for_backward(x, h0, a1, y1, a2, h1, a3, y2, a4, h2, a5, mr1, mr2, mr3, mr4, mr5,
+                              *[p[1] for p in packed], *[wn[3 * i] for i in range(6)], *[wn[3 * i + 1] for i in range(6)],
+                              *gam)
+        ctx.meta = (cin, cout, float(wn_eps))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        S = ctx.saved_tensors
+        x, h0, a1, y1, a2, h1, a3, y2, a4, h2, a5, mr1, mr2, mr3, mr4, mr5 = S[:16]
+        wb, vs, gs, gam = S[16:22], S[22:28], S[28:34], S[34:39]
+        cin, cout, wn_eps = ctx.meta
+        gout = L.dev(gout, 'grad params')
+        gw, gb, ggam, gbet = [None] * 6, [None] * 6, [None] * 5, [None] * 5
+        # out block
+        gw[5], gb[5] = _wgrad(gout, a5, F32, cout, 1)
+        ga, _ = _conv(gout, wb[5], None, None, cout, F32, 1, False)
+        G, ggam[4], gbet[4] = _bn_relu_bwd(ga, a5, h2, mr5, gam[4], None)
+        # residual blocks, last first: (layer indices, BatchNorm indices, activations)
+        for (l2, l1, bB, bA, aB, yB, mrB, aA, hA, mrA) in ((4, 3, 3, 2, a4, y2, mr4, a3, h1, mr3),
+                                                          (2, 1, 1, 0, a2, y1, mr2, a1, h0, mr1)):
+            gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, 3)
+            ga, _ = _conv(G, wb[l2], None, None, F32, F32, 3, False)
+            gy, ggam[bB], gbet[bB] = _bn_relu_bwd(ga, aB, yB, mrB, gam[bB], None)
+            gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, 3)
+            ga, _ = _conv(gy, wb[l1], None, None, F32, F32, 3, False)
+            G, ggam[bA], gbet[bA] = _bn_relu_bwd(ga, aA, hA, mrA, gam[bA], G)  # + the skip branch
+        gw[0], gb[0] = _wgrad(G, x, cin, F32, 3)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx, _ = _conv(G, wb[0], None, None, F32, cin, 3, False)
+        grads = []
+        for i in range(6):
+            v, g = vs[i], gs[i]
+            gv, gg = torch.empty_like(v), torch.empty_like(g)
+            L.check(L.lib().nfb_wn_bwd(L.ptr(v), L.ptr(g), L.ptr(gw[i]), L.ptr(gv), L.ptr(gg), v.size(0), v[0].numel(),
+                                       wn_eps, L.stream()))
+            grads += [gv, gg, gb[i]]
+        for i in range(5):
+            grads += [ggam[i], gbet[i]]
+        return (gx, None) + tuple(grads) + (None, ) * 10

@@ -132,3 +132,89 @@ def train_step(model, optimizer, x_local, group=None):
     optimizer.step()
     s, n = (float(v) for v in total.tolist())
     return s / n
+
+
+class GraphedTrainStep:
+    """The training step as CUDA-graph replays: graph 1 = train-mode forward + loss + backward (every libnfb200 kernel,
+    the conditioner's cuDNN / cuBLAS calls and torch's glue captured once), then the gradient all-reduce on the flat
+    bucket, then a fused multi-tensor optimizer step (``capturable`` Adam inside graph 2).  The eager step of a Glow K=32
+    is dominated by Python / launch overhead (thousands of small launches); replaying removes it.
+
+    All parameter gradients are views into ONE flat fp32 buffer, so the all-reduce needs no gather / scatter copies and
+    zeroing the gradients is a single memset node of the graph.
+
+    Usage::
+
+        step = GraphedTrainStep(model, torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True), example_batch)
+        loss = step(x_local)          # device tensor holding the global mean NLL; no host sync
+    """
+
+    def __init__(self, model, optimizer, example, group=None, warmup=2):
+        if not example.is_cuda:
+            raise RuntimeError('nfb200: GraphedTrainStep needs CUDA tensors (no CPU fallback)')
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in params), device=example.device, dtype=torch.float32)
+        off = 0
+        for p in params:  # gradients live inside the bucket for good
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.x = example.clone()
+        self.total = torch.zeros(2, device=example.device, dtype=torch.float64)   # (sum NLL, count), all-reduced
+        self.count = torch.ones((), device=example.device, dtype=torch.float32)   # global batch size, device-resident
+        self.loss = torch.zeros((), device=example.device, dtype=torch.float32)
+        self._sync_count()
+        with torch.no_grad():
+            model(self.x)  # ActNorm's data-dependent init (modules.py:238-244) happens here if it has not yet
+        # warm-up steps (allocator, cuDNN plans, optimizer state) must not move the model: snapshot, restore below
+        snap = {k: v.clone() for k, v in model.state_dict().items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):  # outside capture; at least once so the optimizer state exists
+                self._fwd_bwd()
+                self._reduce()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(snap[k])  # in place: the captured graphs keep pointing at the same storage
+            for st in optimizer.state.values():  # fresh optimizer state (step = 0, moments = 0), same storage
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt):
+            optimizer.step()
+
+    def _sync_count(self):
+        n = torch.tensor([float(self.x.size(0))], device=self.x.device, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(n, group=self.group)
+        self.count.copy_(n[0].float())
+
+    def _fwd_bwd(self):
+        self.flat.zero_()
+        rows, total = self.model.nll(self.x)
+        self.total.copy_(total)
+        (rows.sum() / self.count).backward()  # gradients accumulate into the views of the flat bucket
+
+    def _reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, group=self.group)
+            dist.all_reduce(self.total, group=self.group)
+        self.loss.copy_((self.total[0] / self.total[1]).float())
+
+    def __call__(self, x_local):
+        if x_local.shape != self.x.shape:
+            raise RuntimeError('nfb200: GraphedTrainStep was captured for batches of shape %s' % (tuple(self.x.shape), ))
+        self.x.copy_(x_local, non_blocking=True)
+        self.g_fb.replay()
+        self._reduce()
+        self.g_opt.replay()
+        return self.loss

@@ -9,6 +9,8 @@ import nfb200  # noqa: E402
 import nfb200._lib as L  # noqa: E402
 import bench  # noqa: E402
 
+torch.set_grad_enabled(False)  # inference kernels; the gradient kernels below are called through the C ABI directly
+
 peaks = bench.load_peaks()
 B, dims = 16384, (3, 32, 32)
 D = 3072
@@ -71,6 +73,49 @@ cases.append(('squeeze2d 3x32x32', lambda: L.check(L.lib().nfb_squeeze2d(z.data_
 nr = torch.empty(B, device='cuda')
 tot = torch.empty(2, device='cuda', dtype=torch.float64)
 cases.append(('gauss_nll 3x32x32', lambda: L.check(L.lib().nfb_gauss_nll(z.data_ptr(), ldj.data_ptr(), nr.data_ptr(), tot.data_ptr(), B, D, st)), 4 * D + 8, B))
+# ---- gradient kernels (csrc/backward.cu): bytes = tensors read + written once ---------------------------------------
+gy = torch.randn((B, ) + dims, device='cuda')
+gz = torch.empty_like(z)
+gp = torch.empty_like(params)
+gl = torch.randn(B, device='cuda')
+gs = torch.empty(2, device='cuda')
+scr = torch.empty(2 * 3072, device='cuda', dtype=torch.float64)
+
+
+def affine_bwd(mode, C, H, W):
+    return lambda: L.check(L.lib().nfb_affine_coupling_bwd(z.data_ptr(), params.data_ptr(), gy.data_ptr(), gl.data_ptr(),
+                                                         gz.data_ptr(), gp.data_ptr(), gs.data_ptr(), gs.data_ptr() + 4,
+                                                         scr.data_ptr(), a.data_ptr(), b.data_ptr(), B, C, H, W, mode, 0, st))
+
+
+# reads z (4D) + s_raw (2D) + gy (4D), writes gz (4D) + gparams (4D) = 18 D
+cases.append(('affine BWD checker 3x32x32', affine_bwd(L.SPLIT_CHECKER, 3, 32, 32), 18 * D + 4))
+cases.append(('affine BWD channel 12x16x16', affine_bwd(L.SPLIT_CHANNEL, 12, 16, 16), 18 * D + 4))
+cases.append(('affine BWD 1d 3072', affine_bwd(L.SPLIT_1D, 3072, 1, 1), 18 * D + 4))
+ls3 = torch.zeros(3, device='cuda')
+g3 = torch.empty(6, device='cuda')
+cases.append(('actnorm BWD 3x32x32', lambda: L.check(L.lib().nfb_actnorm_bwd(
+    gy.data_ptr(), z.data_ptr(), gl.data_ptr(), ls3.data_ptr(), ls3.data_ptr(), gz.data_ptr(), g3.data_ptr(), g3.data_ptr() + 12,
+    scr.data_ptr(), B, 3, 1024, st)), 12 * D + 4))
+z48 = z.view(B, 48, 8, 8)
+W48 = torch.randn(48, 48, device='cuda') / 7
+gW = torch.empty(48, 48, device='cuda')
+cases.append(('invconv wgrad C=48 8x8', lambda: L.check(L.lib().nfb_invconv1x1_wgrad(
+    gy.data_ptr(), z48.data_ptr(), gW.data_ptr(), B, 48, 64, st)), 8 * D))
+cases.append(('invconv apply (W^T gy) C=48 8x8', lambda: L.check(L.lib().nfb_invconv1x1_apply(
+    gy.data_ptr(), gz.data_ptr(), None, None, W48.data_ptr(), None, 0.0, B, 48, 64, st)), 8 * D))
+gym = torch.randn_like(zm)
+gzm = torch.empty_like(zm)
+glm = torch.randn(Bm, device='cuda')
+gpm = torch.empty_like(pm)
+cases.append(('mixlog BWD K=8 checker 3x32x32 (B=4096)', lambda: L.check(L.lib().nfb_mixlog_coupling_bwd(
+    zm.data_ptr(), pm.data_ptr(), gym.data_ptr(), glm.data_ptr(), gzm.data_ptr(), gpm.data_ptr(), gs.data_ptr(),
+    gs.data_ptr() + 4, scr.data_ptr(), a.data_ptr(), b.data_ptr(), Bm, 3, 32, 32, L.SPLIT_CHECKER, 0, K, st)),
+    (12 + 2 * 2 * (2 + 3 * K)) * D + 4, Bm))  # z, gy, gz (12 D) + params and gparams ((2+3K) * D/2 * 4 each)
+gpr = torch.empty_like(pr)
+cases.append(('rqs BWD K=8 checker 3x32x32 (B=4096)', lambda: L.check(L.lib().nfb_rqs_coupling_bwd(
+    zm.data_ptr(), pr.data_ptr(), gym.data_ptr(), glm.data_ptr(), gzm.data_ptr(), gpr.data_ptr(), Bm, 3, 32, 32,
+    L.SPLIT_CHECKER, 0, K, 3.0, st)), (12 + 2 * 2 * (3 * K - 1)) * D + 4, Bm))
 for case in cases:
     name, fn, bytes_per_sample = case[:3]
     nb = case[3] if len(case) > 3 else B

@@ -74,3 +74,70 @@ def test_allreduce_is_noop_without_process_group():
     t = torch.tensor([3.0, 2.0], dtype=torch.float64)
     assert parallel.allreduce_nll(t) is t
     assert parallel.global_bits_per_dim(t, 1) == pytest.approx(1.5 / 0.6931471805599453)
+
+
+# ---- data-parallel training step: flat-bucket gradient all-reduce (nfb200.parallel.train_step) -------------------------
+class _OracleFlow(torch.nn.Module):
+    """A CPU stand-in with the product models' interface (``nll(x) -> (rows, total)``), built on the oracle stack, so the
+    host-side logic of train_step / allreduce_gradients can run under gloo.  (The CUDA layers themselves: -m gpu tests.)"""
+
+    def __init__(self, spec, sd):
+        super().__init__()
+        self.spec = spec
+        self.keys = [k for k, v in sd.items() if v.is_floating_point() and k.split('.')[-1] in ('s_log_scale', 's_bias', 'weight_g', 'weight_v', 'bias', 'weight')]
+        self.params = torch.nn.ParameterList([torch.nn.Parameter(sd[k].clone()) for k in self.keys])
+        self.rest = {k: v for k, v in sd.items() if k not in self.keys}
+
+    def nll(self, x):
+        from oracle import flow_oracle as O
+        sd = dict(self.rest)
+        sd.update({k: p for k, p in zip(self.keys, self.params)})
+        z, ldj = O.stack_forward(self.spec, sd, x)
+        zf = z.reshape(z.shape[0], -1)
+        rows = 0.5 * (zf * zf).sum(1) + 0.5 * zf.shape[1] * 1.8378770664093453 - ldj
+        total = torch.tensor([float(rows.sum()), float(rows.numel())], dtype=torch.float64)
+        return rows, total
+
+
+def _train_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nfb200 import parallel
+        from oracle import flow_oracle as O
+        from tests import _golden
+        meta, a, sd = _golden.load('model_realnvp_64d')
+        spec = O.stack_spec('realnvp', tuple(meta['dims']), meta['datatype'], meta['layers'])
+        x = a['x'][:37]  # uneven split 19 + 18
+        net = _OracleFlow(spec, sd)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+        losses = [parallel.train_step(net, opt, parallel.shard_rows(x, rank, world)) for _ in range(3)]
+        if rank == 0:
+            torch.save({'losses': losses, 'params': [p.detach().clone() for p in net.params]}, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_train_step_matches_single_process(tmp_path):
+    """Two ranks with uneven shards take the same optimisation steps as one process on the whole batch."""
+    sys.path.insert(0, ROOT)
+    from nfb200 import parallel
+    from oracle import flow_oracle as O
+    from tests import _golden
+    out = str(tmp_path / 'train.pt')
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    meta, a, sd = _golden.load('model_realnvp_64d')
+    spec = O.stack_spec('realnvp', tuple(meta['dims']), meta['datatype'], meta['layers'])
+    net = _OracleFlow(spec, sd)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    torch.set_num_threads(2)
+    losses = [parallel.train_step(net, opt, a['x'][:37]) for _ in range(3)]
+    for l0, l1 in zip(losses, res['losses']):
+        assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    assert losses[-1] < losses[0]
+    for p0, p1 in zip(net.params, res['params']):
+        assert torch.allclose(p0, p1, rtol=1e-4, atol=1e-6)
