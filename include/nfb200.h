@@ -280,31 +280,34 @@ int nfb_gauss_nll_bwd(const float* z, const float* g_rows, float* gz, float* gld
 
 /* WeightNorm (weight_norm.py:40) of v (O, I, KK) / g (I, KK), KK in {1, 9}: w_nat (O, I, KK) plus the two packed layouts
  * the convolution kernel reads -- w_fwd [O/32][I/32][32 ci][KK][32 o] and, for the data gradient, w_bwd
- * [I/32][O/32][32 o][KK flipped][32 i].  Both packed buffers (ceil(O/32)*ceil(I/32)*32*KK*32 floats) must be zero-filled
- * by the caller (padding). */
+ * [I/32][O/32][32 o][KK flipped][32 i].  Both packed buffers hold ceil(O/32)*ceil(I/32)*32*KK*32 floats; the padding
+ * is written (as zeros) by the call. */
 int nfb_wn_pack_train(const float* v, const float* g, float* w_nat, float* w_fwd, float* w_bwd, int O, int I, int KK,
                       float eps, nfb_stream_t stream);
 /* gradient of that map: gw (O, I*KK) -> gv (O, I*KK), gg (I*KK). */
 int nfb_wn_bwd(const float* v, const float* g, const float* gw, float* gv, float* gg, int O, int Ikk, float eps,
                nfb_stream_t stream);
 /* out (B, Cout, h, w) = conv_ks(in (B, Cin, h, w); packed w) + bias (+ skip); ks in {1, 3}, padding ks/2.  stats (device
- * double[2*Cout], may be NULL, zeroed by the call): per-channel sum and sum of squares of `out` for the BatchNorm that
- * follows.  The data gradient of a layer is the same call with w_bwd and Cin / Cout exchanged. */
+ * double[2*Cout], may be NULL): per-channel sum and sum of squares of `out` for the BatchNorm that follows, accumulated
+ * with fp64 atomics; zeroed by the call unless stats_zeroed != 0 (the caller carved it from one zero-filled arena).  The
+ * data gradient of a layer is the same call with w_bwd and Cin / Cout exchanged. */
 int nfb_conv_train(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, double* stats,
-                   int B, int Cin, int Cout, int h, int w, int ks, nfb_stream_t stream);
+                   int stats_zeroed, int B, int Cin, int Cout, int h, int w, int ks, nfb_stream_t stream);
 /* gw (Cout, Cin, ks, ks) = sum over batch and pixels of gy (B, Cout, h, w) x a (B, Cin, h, w); gb (Cout, may be NULL) =
- * sum of gy.  Both zeroed by the call; fp32 atomics across sample groups. */
-int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, float* gb, int B, int Cin, int Cout, int h, int w,
-                         int ks, nfb_stream_t stream);
+ * sum of gy.  Sample groups write partial sums into `scratch` (nfb_conv_train_wgrad_scratch floats, need not be zeroed)
+ * and a second kernel adds them up: no atomics, deterministic. */
+long long nfb_conv_train_wgrad_scratch(int B, int Cin, int Cout, int h, int w, int ks);
+int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, float* gb, float* scratch, int B, int Cin, int Cout,
+                         int h, int w, int ks, nfb_stream_t stream);
 /* a = relu(BatchNorm_train(x)) from the moments `stats` (sum | sum of squares over batch and pixels); stores
  * mean_rstd (float[2C]) for the backward pass and updates running_mean / running_var (may be NULL) with `momentum`
  * (running_var takes the unbiased variance, like nn.BatchNorm2d). */
 int nfb_bn_relu_fwd(const float* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* a_out, float* mean_rstd, int B, int C, int HW,
                     nfb_stream_t stream);
-/* U = ga * [a > 0]; sums (device double[2C], zeroed by the call) = (sum U | sum U * xhat). */
+/* U = ga * [a > 0]; sums (device double[2C], zeroed by the call unless sums_zeroed != 0) = (sum U | sum U * xhat). */
 int nfb_bn_relu_bwd_reduce(const float* ga, const float* a, const float* x, const float* mean_rstd, float* U, double* sums,
-                           int B, int C, int HW, nfb_stream_t stream);
+                           int sums_zeroed, int B, int C, int HW, nfb_stream_t stream);
 /* gx = gamma * rstd * (U - mean(U) - xhat * mean(U xhat)) (+ add, may be NULL); g_gamma = sum U xhat, g_beta = sum U. */
 int nfb_bn_bwd_apply(const float* U, const float* x, const float* mean_rstd, const float* gamma, const double* sums,
                      const float* add, float* gx, float* g_gamma, float* g_beta, int B, int C, int HW, nfb_stream_t stream);

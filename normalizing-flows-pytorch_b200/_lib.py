@@ -68,13 +68,15 @@ _SIGNATURES = {
     'nfb_gauss_nll_bwd': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_wn_pack_train': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     'nfb_wn_bwd': [_P, _P, _P, _P, _P, _I, _I, _F, _P],
-    'nfb_conv_train': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    'nfb_conv_train_wgrad': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_conv_train': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_conv_train_wgrad': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_conv_train_wgrad_scratch': [_I, _I, _I, _I, _I, _I],
     'nfb_bn_relu_fwd': [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P],
-    'nfb_bn_relu_bwd_reduce': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_bn_relu_bwd_reduce': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     'nfb_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
-_RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong}
+_RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong,
+             'nfb_conv_train_wgrad_scratch': ctypes.c_longlong}
 
 _lib = None
 

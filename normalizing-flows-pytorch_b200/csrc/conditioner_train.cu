@@ -20,21 +20,37 @@ namespace nfb {
 //   w_fwd [oc][ic][ci 32][tap][o 32]      forward conv: 32-output x 32-input chunks, zero padded (caller zero-fills)
 //   w_bwd [ic'][oc'][o 32][KK-1-tap][i 32] data-gradient conv: roles of O and I swapped, taps flipped
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) wn_pack_train_kernel(const float* __restrict__ v, const float* __restrict__ gw,
+// block = 32 columns j (threadIdx.x) x 8 row slices (threadIdx.y: o = y, y+8, ...); the column norm is reduced through
+// shared memory.  Padding entries of the packed layouts (o >= O or i >= I inside a 32 x 32 chunk) are written as zeros,
+// so the caller needs no zero-fill.
+__global__ void __launch_bounds__(256) wn_pack_train_kernel(const float* __restrict__ v, const float* __restrict__ gw,
                                                            float* __restrict__ w_nat, float* __restrict__ w_fwd,
                                                            float* __restrict__ w_bwd, int O, int I, int KK, float eps) {
+    __shared__ float part[8][33];
     const int J = I * KK;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
-    float ss = 0.f;
-    for (int o = 0; o < O; ++o) { const float x = __ldg(v + static_cast<size_t>(o) * J + j); ss = fmaf(x, x, ss); }
-    const float scale = __fdiv_rn(__ldg(gw + j), __fadd_rn(sqrtf(ss), eps));
-    const int i = j / KK, tap = j - i * KK;
     const int n_ic = (I + 31) >> 5, n_oc = (O + 31) >> 5;
+    const int Jp = n_ic * 32 * KK, Op = n_oc * 32;
+    const int j = blockIdx.x * 32 + threadIdx.x;   // column in the padded (I_pad * KK) range
+    const int ty = threadIdx.y;
+    const bool col = j < J;
+    float ss = 0.f;
+    if (col)
+        for (int o = ty; o < O; o += 8) { const float x = __ldg(v + static_cast<size_t>(o) * J + j); ss = fmaf(x, x, ss); }
+    part[ty][threadIdx.x] = ss;
+    __syncthreads();
+    if (j >= Jp) return;
+    ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss += part[k][threadIdx.x];
+    const float scale = col ? __fdiv_rn(__ldg(gw + j), __fadd_rn(sqrtf(ss), eps)) : 0.f;
+    const int i = j / KK, tap = j - i * KK;
     const size_t chunk = static_cast<size_t>(32) * KK * 32;
-    for (int o = 0; o < O; ++o) {
-        const float w = __fmul_rn(__ldg(v + static_cast<size_t>(o) * J + j), scale);
-        w_nat[static_cast<size_t>(o) * J + j] = w;
+    for (int o = ty; o < Op; o += 8) {
+        float w = 0.f;
+        if (col && o < O) {
+            w = __fmul_rn(__ldg(v + static_cast<size_t>(o) * J + j), scale);
+            w_nat[static_cast<size_t>(o) * J + j] = w;
+        }
         w_fwd[(static_cast<size_t>(o >> 5) * n_ic + (i >> 5)) * chunk + ((i & 31) * KK + tap) * 32 + (o & 31)] = w;
         w_bwd[(static_cast<size_t>(i >> 5) * n_oc + (o >> 5)) * chunk + ((o & 31) * KK + (KK - 1 - tap)) * 32 + (i & 31)] = w;
     }
@@ -42,24 +58,33 @@ __global__ void __launch_bounds__(128) wn_pack_train_kernel(const float* __restr
 
 // gradient of the WeightNorm map: s_j = g_j / (n_j + eps), n_j = ||v[:, j]||, d_j = sum_o gw[o,j] v[o,j]
 //   gg_j = d_j / (n_j + eps);   gv[o,j] = gw[o,j] s_j - v[o,j] d_j g_j / ((n_j + eps)^2 n_j)
-__global__ void __launch_bounds__(128) wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                                     const float* __restrict__ gw, float* __restrict__ gv,
                                                     float* __restrict__ gg, int O, int J, float eps) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
+    __shared__ float p_ss[8][33], p_d[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int ty = threadIdx.y;
     float ss = 0.f, d = 0.f;
-    for (int o = 0; o < O; ++o) {
-        const float x = __ldg(v + static_cast<size_t>(o) * J + j);
-        ss = fmaf(x, x, ss);
-        d = fmaf(__ldg(gw + static_cast<size_t>(o) * J + j), x, d);
-    }
+    if (j < J)
+        for (int o = ty; o < O; o += 8) {
+            const float x = __ldg(v + static_cast<size_t>(o) * J + j);
+            ss = fmaf(x, x, ss);
+            d = fmaf(__ldg(gw + static_cast<size_t>(o) * J + j), x, d);
+        }
+    p_ss[ty][threadIdx.x] = ss;
+    p_d[ty][threadIdx.x] = d;
+    __syncthreads();
+    if (j >= J) return;
+    ss = d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ss += p_ss[k][threadIdx.x]; d += p_d[k][threadIdx.x]; }
     const float n = sqrtf(ss), ne = n + eps, gj = __ldg(g + j);
-    const float s = gj / ne;
+    const float sc = gj / ne;
     const float c = n > 0.f ? d * gj / (ne * ne * n) : 0.f;
-    gg[j] = d / ne;
-    for (int o = 0; o < O; ++o) {
+    if (ty == 0) gg[j] = d / ne;
+    for (int o = ty; o < O; o += 8) {
         const size_t k = static_cast<size_t>(o) * J + j;
-        gv[k] = fmaf(__ldg(gw + k), s, -__ldg(v + k) * c);
+        gv[k] = fmaf(__ldg(gw + k), sc, -__ldg(v + k) * c);
     }
 }
 
@@ -189,7 +214,8 @@ static int launch_conv_layer(const ConvArgs& A, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------------
 // weight gradient: gw[o, ci, tap] = sum_{b,y,x} gy[b,o,y,x] a[b,ci,y+dy-1,x+dx-1];  gb[o] = sum gy[b,o,y,x]
 // CTA = one (32 o) x (32 ci) chunk pair x a group of samples; thread = 2 o x 2 ci x KK accumulators; one image row of gy
-// and three rows of a live in registers at a time.  Partial sums -> fp32 atomics on the natural-layout gradient.
+// and three rows of a live in registers at a time.  Every sample group writes its partial gradient (natural layout, then
+// the bias partial) with plain stores; wgrad_reduce_kernel sums the groups -- no atomics, deterministic.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int W>
 __device__ __forceinline__ void load_row(float (&dst)[W], const float* __restrict__ p) {
@@ -202,8 +228,7 @@ __device__ __forceinline__ void load_row(float (&dst)[W], const float* __restric
 
 template <int H, int W, int KS>
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ a,
-                                                   float* __restrict__ gw, float* __restrict__ gb, int Cin, int Cout,
-                                                   int B, int spc) {
+                                                   float* __restrict__ partial, int Cin, int Cout, int B, int spc) {
     constexpr int KK = KS * KS;
     constexpr int GS = H * W + 4;          // channel stride of the gy tile  (stride/4 odd: conflict-free float4 reads)
     constexpr int AS = (H + 2) * W + 4;    // channel stride of the a tile (zero rows above / below)
@@ -270,19 +295,41 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy
             }
         }
     }
+    const size_t n_w = static_cast<size_t>(Cout) * Cin * KK;
+    float* pw = partial + blockIdx.x * (n_w + Cout);  // this sample group's partial: gw (natural layout) | gb
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int o = oc * 32 + op + 16 * i;
         if (o >= Cout) continue;
-        if (gb && cp == 0 && ic == 0) atomicAdd(gb + o, gbacc[i]);
+        if (cp == 0 && ic == 0) pw[n_w + o] = gbacc[i];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int ci = ic * 32 + cp + 16 * j;
             if (ci >= Cin) continue;
 #pragma unroll
-            for (int k = 0; k < KK; ++k) atomicAdd(gw + (static_cast<size_t>(o) * Cin + ci) * KK + k, acc[i][j][k]);
+            for (int k = 0; k < KK; ++k) pw[(static_cast<size_t>(o) * Cin + ci) * KK + k] = acc[i][j][k];
         }
     }
+}
+
+// gw[i] = sum over groups of partial[g][i] (i < n_w), gb[i - n_w] likewise
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw,
+                                                          float* __restrict__ gb, int n_w, int n_b, int groups) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_w + n_b) return;
+    const size_t stride = static_cast<size_t>(n_w) + n_b;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int g = 0;
+    for (; g + 4 <= groups; g += 4) {
+        a0 += __ldg(partial + (g + 0) * stride + i);
+        a1 += __ldg(partial + (g + 1) * stride + i);
+        a2 += __ldg(partial + (g + 2) * stride + i);
+        a3 += __ldg(partial + (g + 3) * stride + i);
+    }
+    for (; g < groups; ++g) a0 += __ldg(partial + g * stride + i);
+    const float r = (a0 + a1) + (a2 + a3);
+    if (i < n_w) gw[i] = r;
+    else if (gb) gb[i - n_w] = r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -419,7 +466,8 @@ extern "C" int nfb_wn_pack_train(const float* v, const float* g, float* w_nat, f
                                  int KK, float eps, nfb_stream_t stream) {
     if (!v || !g || !w_nat || !w_fwd || !w_bwd) return NFB_ERR_NULL;
     if (O <= 0 || I <= 0 || (KK != 1 && KK != 9)) return NFB_ERR_SHAPE;
-    wn_pack_train_kernel<<<(I * KK + 127) / 128, 128, 0, as_stream(stream)>>>(v, g, w_nat, w_fwd, w_bwd, O, I, KK, eps);
+    const int Jp = ((I + 31) / 32) * 32 * KK;
+    wn_pack_train_kernel<<<(Jp + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(v, g, w_nat, w_fwd, w_bwd, O, I, KK, eps);
     return launch_status();
 }
 
@@ -427,17 +475,18 @@ extern "C" int nfb_wn_bwd(const float* v, const float* g, const float* gw, float
                           nfb_stream_t stream) {
     if (!v || !g || !gw || !gv || !gg) return NFB_ERR_NULL;
     if (O <= 0 || Ikk <= 0) return NFB_ERR_SHAPE;
-    wn_bwd_kernel<<<(Ikk + 127) / 128, 128, 0, as_stream(stream)>>>(v, g, gw, gv, gg, O, Ikk, eps);
+    wn_bwd_kernel<<<(Ikk + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(v, g, gw, gv, gg, O, Ikk, eps);
     return launch_status();
 }
 
 extern "C" int nfb_conv_train(const float* in, const float* w_packed, const float* bias, const float* skip, float* out,
-                              double* stats, int B, int Cin, int Cout, int h, int w, int ks, nfb_stream_t stream) {
+                              double* stats, int stats_zeroed, int B, int Cin, int Cout, int h, int w, int ks,
+                              nfb_stream_t stream) {
     if (!in || !w_packed || !out) return NFB_ERR_NULL;
     if (B <= 0 || Cin <= 0 || Cout <= 0 || (ks != 1 && ks != 3)) return NFB_ERR_SHAPE;
     if (!aligned16(in) || !aligned16(out) || !aligned16(w_packed) || (skip && !aligned16(skip))) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (stats) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, st);
+    if (stats && !stats_zeroed) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, st);
     const ConvArgs A{in, w_packed, bias, skip, out, stats, Cin, Cout, B};
 #define NFB_CL(H_, W_, NT_, OCT_)                                                     \
     return ks == 3 ? launch_conv_layer<H_, W_, NT_, OCT_, 3>(A, st) : launch_conv_layer<H_, W_, NT_, OCT_, 1>(A, st)
@@ -448,18 +497,34 @@ extern "C" int nfb_conv_train(const float* in, const float* w_packed, const floa
     return NFB_ERR_UNSUPPORTED;
 }
 
-extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, float* gb, int B, int Cin, int Cout, int h,
-                                    int w, int ks, nfb_stream_t stream) {
-    if (!gy || !a || !gw) return NFB_ERR_NULL;
+// samples per CTA: large enough that the partial-sum traffic (groups x |gw|) stays small next to the FMA work
+static int wgrad_spc(int B, int Cin, int Cout, int h, int w) {
+    const int pairs = ((Cin + 31) / 32) * ((Cout + 31) / 32);
+    int spc = h * w >= 256 ? 2 : (h * w >= 64 ? 4 : 16);
+    const int fill = (B * pairs + kSMs * 2 - 1) / (kSMs * 2);  // never more than about two CTAs per SM in total
+    if (spc < fill) spc = fill;
+    if (spc > B) spc = B;
+    return spc < 1 ? 1 : spc;
+}
+
+extern "C" long long nfb_conv_train_wgrad_scratch(int B, int Cin, int Cout, int h, int w, int ks) {
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || (ks != 1 && ks != 3)) return NFB_ERR_SHAPE;
+    const int spc = wgrad_spc(B, Cin, Cout, h, w);
+    const long long groups = (B + spc - 1) / spc;
+    return groups * (static_cast<long long>(Cout) * Cin * ks * ks + Cout);
+}
+
+extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, float* gb, float* scratch, int B, int Cin,
+                                    int Cout, int h, int w, int ks, nfb_stream_t stream) {
+    if (!gy || !a || !gw || !scratch) return NFB_ERR_NULL;
     if (B <= 0 || Cin <= 0 || Cout <= 0 || (ks != 1 && ks != 3)) return NFB_ERR_SHAPE;
     if (!aligned16(gy) || !aligned16(a)) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(gw, 0, sizeof(float) * static_cast<size_t>(Cout) * Cin * ks * ks, st);
-    if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * Cout, st);
     const int pairs = ((Cin + 31) / 32) * ((Cout + 31) / 32);
-    int spc = (B * pairs + kSMs * 2 - 1) / (kSMs * 2);  // about two CTAs per SM in total
-    if (spc < 1) spc = 1;
-    dim3 grid((B + spc - 1) / spc, pairs);
+    const int spc = wgrad_spc(B, Cin, Cout, h, w);
+    const int groups = (B + spc - 1) / spc;
+    dim3 grid(groups, pairs);
+    int rc = NFB_ERR_UNSUPPORTED;
 #define NFB_WG(H_, W_)                                                                                       \
     do {                                                                                                     \
         constexpr size_t smem = sizeof(float) * 32 * ((H_) * (W_) + 4 + ((H_) + 2) * (W_) + 4);             \
@@ -469,15 +534,18 @@ extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, 
             cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
             attr_set = true;                                                                                 \
         }                                                                                                    \
-        if (ks == 3) wgrad_kernel<H_, W_, 3><<<grid, 256, smem, st>>>(gy, a, gw, gb, Cin, Cout, B, spc);     \
-        else wgrad_kernel<H_, W_, 1><<<grid, 256, smem, st>>>(gy, a, gw, gb, Cin, Cout, B, spc);             \
-        return launch_status();                                                                              \
+        if (ks == 3) wgrad_kernel<H_, W_, 3><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);    \
+        else wgrad_kernel<H_, W_, 1><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);            \
+        rc = launch_status();                                                                                \
     } while (0)
     if (h == 16 && w == 16) NFB_WG(16, 16);
-    if (h == 8 && w == 8) NFB_WG(8, 8);
-    if (h == 4 && w == 4) NFB_WG(4, 4);
+    else if (h == 8 && w == 8) NFB_WG(8, 8);
+    else if (h == 4 && w == 4) NFB_WG(4, 4);
 #undef NFB_WG
-    return NFB_ERR_UNSUPPORTED;
+    if (rc != NFB_OK) return rc;
+    const int n_w = Cout * Cin * ks * ks;
+    wgrad_reduce_kernel<<<(n_w + Cout + 255) / 256, 256, 0, st>>>(scratch, gw, gb, n_w, Cout, groups);
+    return launch_status();
 }
 
 extern "C" int nfb_bn_relu_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
@@ -493,12 +561,12 @@ extern "C" int nfb_bn_relu_fwd(const float* x, const double* stats, const float*
 }
 
 extern "C" int nfb_bn_relu_bwd_reduce(const float* ga, const float* a, const float* x, const float* mean_rstd, float* U,
-                                      double* sums, int B, int C, int HW, nfb_stream_t stream) {
+                                      double* sums, int sums_zeroed, int B, int C, int HW, nfb_stream_t stream) {
     if (!ga || !a || !x || !mean_rstd || !U || !sums) return NFB_ERR_NULL;
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (HW % 4 || C > 1024 || !aligned16(ga) || !aligned16(a) || !aligned16(x) || !aligned16(U)) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (!sums_zeroed) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     const long long nv = static_cast<long long>(B) * C * HW / 4;
     bn_relu_bwd_reduce_kernel<<<ew_grid(nv), 256, sizeof(float) * 2 * C, st>>>(ga, a, x, mean_rstd, U, sums, B, C, HW);
     return launch_status();

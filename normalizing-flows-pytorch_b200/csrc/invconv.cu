@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) invconv_weight_kernel(const float* __rest
     for (int i = threadIdx.x; i < C; i += blockDim.x) diag[i] = __fmul_rn(__ldg(sign_s + i), expf(__ldg(log_s + i)));
     __syncthreads();
     // W[r,c] = sum_k P[r,k] (L' U')[k,c]   (modules.py:473).  P is a permutation, so only one k contributes.
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * C; i += gridDim.x * blockDim.x) {  // all CTAs share W
         const int r = i / C, c = i - r * C;
         float acc = 0.f;
         for (int k = 0; k < C; ++k) {
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) invconv_weight_kernel(const float* __rest
         }
         W[i] = acc;
     }
-    if (Winv == nullptr) return;
+    if (Winv == nullptr || blockIdx.x != 0) return;  // the inverse (fp64 substitution, thread per column) stays on CTA 0
     // W^-1 = U'^-1 L'^-1 P^T.  Thread j solves W x = e_j: forward then backward substitution, all in fp64,
     // rounded to fp32 once.  Replaces the per-pixel lu_solve of modules.py:490 by one matrix apply.
     for (int j = threadIdx.x; j < C; j += blockDim.x) {
@@ -237,7 +237,8 @@ extern "C" int nfb_invconv1x1_weight(const float* P, const float* L, const float
     if (!P || !L || !U || !log_s || !sign_s || !W_out) return NFB_ERR_NULL;
     if (C <= 0) return NFB_ERR_SHAPE;
     if (C > kMaxInvconvC) return NFB_ERR_UNSUPPORTED;
-    invconv_weight_kernel<<<1, 256, 0, as_stream(stream)>>>(P, L, U, log_s, sign_s, W_out, Winv_out, C);
+    const int ctas = (C * C + 255) / 256 < 64 ? (C * C + 255) / 256 : 64;
+    invconv_weight_kernel<<<ctas, 256, 0, as_stream(stream)>>>(P, L, U, log_s, sign_s, W_out, Winv_out, C);
     return launch_status();
 }
 

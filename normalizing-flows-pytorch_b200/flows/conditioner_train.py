@@ -21,13 +21,16 @@ SUPPORTED_HW = ((16, 16), (8, 8), (4, 4))
 F32 = 32  # base_filters
 
 
-def _conv(x, w_packed, bias, skip, cin, cout, ks, want_stats):
+def _conv(x, w_packed, bias, skip, cin, cout, ks, want_stats, stats=None):
+    """`stats`: a pre-zeroed double[2*cout] slice of the caller's accumulator arena (one fill for the whole network)."""
     B, _, h, w = x.shape
     out = torch.empty((B, cout, h, w), device=x.device, dtype=torch.float32)
-    stats = torch.empty(2 * cout, device=x.device, dtype=torch.float64) if want_stats else None
+    zeroed = stats is not None
+    if want_stats and stats is None:
+        stats = torch.empty(2 * cout, device=x.device, dtype=torch.float64)
     L.check(L.lib().nfb_conv_train(L.ptr(x), L.ptr(w_packed), L.ptr(bias) if bias is not None else None,
                                    L.ptr(skip) if skip is not None else None, L.ptr(out),
-                                   stats.data_ptr() if want_stats else None, B, cin, cout, h, w, ks, L.stream()))
+                                   stats.data_ptr() if want_stats else None, int(zeroed), B, cin, cout, h, w, ks, L.stream()))
     return out, stats
 
 
@@ -44,17 +47,24 @@ def _wgrad(gy, a, cin, cout, ks):
     B, _, h, w = gy.shape
     gw = torch.empty((cout, cin, ks, ks), device=gy.device, dtype=torch.float32)
     gb = torch.empty(cout, device=gy.device, dtype=torch.float32)
-    L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), B, cin, cout, h, w, ks, L.stream()))
+    n = int(L.lib().nfb_conv_train_wgrad_scratch(B, cin, cout, h, w, ks))
+    if n < 0:
+        L.check(n)
+    scratch = torch.empty(n, device=gy.device, dtype=torch.float32)  # per-sample-group partial sums (no zero-fill needed)
+    L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), L.ptr(scratch), B, cin, cout, h, w, ks,
+                                         L.stream()))
     return gw, gb
 
 
-def _bn_relu_bwd(ga, a, x, mr, gamma, add):
+def _bn_relu_bwd(ga, a, x, mr, gamma, add, sums=None):
     """-> (gx, g_gamma, g_beta): ReLU mask, the two batch sums, then the BatchNorm input gradient (+ residual branch)."""
     B, C, h, w = x.shape
     U = torch.empty_like(x)
-    sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
-    L.check(L.lib().nfb_bn_relu_bwd_reduce(L.ptr(ga), L.ptr(a), L.ptr(x), L.ptr(mr), L.ptr(U), sums.data_ptr(), B, C, h * w,
-                                           L.stream()))
+    zeroed = sums is not None
+    if sums is None:
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    L.check(L.lib().nfb_bn_relu_bwd_reduce(L.ptr(ga), L.ptr(a), L.ptr(x), L.ptr(mr), L.ptr(U), sums.data_ptr(), int(zeroed),
+                                           B, C, h * w, L.stream()))
     gx = torch.empty_like(x)
     gg, gb = torch.empty_like(gamma), torch.empty_like(gamma)
     L.check(L.lib().nfb_bn_bwd_apply(L.ptr(U), L.ptr(x), L.ptr(mr), L.ptr(gamma), sums.data_ptr(),
@@ -77,8 +87,8 @@ class ConvNetTrainFn(Function):
             O, I, KK = v.size(0), v.size(1), v[0, 0].numel()
             n = ((O + 31) // 32) * ((I + 31) // 32) * 32 * KK * 32
             w_nat = torch.empty_like(v)
-            w_fwd = torch.zeros(n, device=v.device, dtype=torch.float32)
-            w_bwd = torch.zeros(n, device=v.device, dtype=torch.float32)
+            w_fwd = torch.empty(n, device=v.device, dtype=torch.float32)  # padding is written by the kernel
+            w_bwd = torch.empty(n, device=v.device, dtype=torch.float32)
             L.check(L.lib().nfb_wn_pack_train(L.ptr(v), L.ptr(g), L.ptr(w_nat), L.ptr(w_fwd), L.ptr(w_bwd), O, I, KK,
                                               float(wn_eps), L.stream()))
             packed.append((w_fwd, w_bwd))
@@ -88,15 +98,17 @@ class ConvNetTrainFn(Function):
         def bnr(t, st, i):
             return _bn_relu(t, st, gam[i], bet[i], rs[2 * i], rs[2 * i + 1], momentum, bn_eps)
 
-        h0, st = _conv(x, packed[0][0], b[0], None, cin, F32, 3, True)
+        arena = torch.zeros(5 * 2 * F32, device=x.device, dtype=torch.float64)  # the five moment accumulators, one fill
+        acc = [arena[i * 2 * F32:(i + 1) * 2 * F32] for i in range(5)]
+        h0, st = _conv(x, packed[0][0], b[0], None, cin, F32, 3, True, acc[0])
         a1, mr1 = bnr(h0, st, 0)
-        y1, st = _conv(a1, packed[1][0], b[1], None, F32, F32, 3, True)
+        y1, st = _conv(a1, packed[1][0], b[1], None, F32, F32, 3, True, acc[1])
         a2, mr2 = bnr(y1, st, 1)
-        h1, st = _conv(a2, packed[2][0], b[2], h0, F32, F32, 3, True)
+        h1, st = _conv(a2, packed[2][0], b[2], h0, F32, F32, 3, True, acc[2])
         a3, mr3 = bnr(h1, st, 2)
-        y2, st = _conv(a3, packed[3][0], b[3], None, F32, F32, 3, True)
+        y2, st = _conv(a3, packed[3][0], b[3], None, F32, F32, 3, True, acc[3])
         a4, mr4 = bnr(y2, st, 3)
-        h2, st = _conv(a4, packed[4][0], b[4], h1, F32, F32, 3, True)
+        h2, st = _conv(a4, packed[4][0], b[4], h1, F32, F32, 3, True, acc[4])
         a5, mr5 = bnr(h2, st, 4)
         out, _ = _conv(a5, packed[5][0], b[5], None, F32, cout, 1, False)
         ctx.save_for_backward(x, h0, a1, y1, a2, h1, a3, y2, a4, h2, a5, mr1, mr2, mr3, mr4, mr5,
@@ -117,16 +129,18 @@ class ConvNetTrainFn(Function):
         # out block
         gw[5], gb[5] = _wgrad(gout, a5, F32, cout, 1)
         ga, _ = _conv(gout, wb[5], None, None, cout, F32, 1, False)
-        G, ggam[4], gbet[4] = _bn_relu_bwd(ga, a5, h2, mr5, gam[4], None)
+        arena = torch.zeros(5 * 2 * F32, device=gout.device, dtype=torch.float64)  # the five BatchNorm-backward sum pairs
+        acc = [arena[i * 2 * F32:(i + 1) * 2 * F32] for i in range(5)]
+        G, ggam[4], gbet[4] = _bn_relu_bwd(ga, a5, h2, mr5, gam[4], None, acc[4])
         # residual blocks, last first: (layer indices, BatchNorm indices, activations)
         for (l2, l1, bB, bA, aB, yB, mrB, aA, hA, mrA) in ((4, 3, 3, 2, a4, y2, mr4, a3, h1, mr3),
                                                           (2, 1, 1, 0, a2, y1, mr2, a1, h0, mr1)):
             gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, 3)
             ga, _ = _conv(G, wb[l2], None, None, F32, F32, 3, False)
-            gy, ggam[bB], gbet[bB] = _bn_relu_bwd(ga, aB, yB, mrB, gam[bB], None)
+            gy, ggam[bB], gbet[bB] = _bn_relu_bwd(ga, aB, yB, mrB, gam[bB], None, acc[bB])
             gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, 3)
             ga, _ = _conv(gy, wb[l1], None, None, F32, F32, 3, False)
-            G, ggam[bA], gbet[bA] = _bn_relu_bwd(ga, aA, hA, mrA, gam[bA], G)  # + the skip branch
+            G, ggam[bA], gbet[bA] = _bn_relu_bwd(ga, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
         gw[0], gb[0] = _wgrad(G, x, cin, F32, 3)
         gx = None
         if ctx.needs_input_grad[0]:

@@ -422,7 +422,7 @@ def test_train_conv_kernels_vs_torch(cin, cout, hw, ks, B):
     n = ((cout + 31) // 32) * ((cin + 31) // 32) * 32 * KK * 32
     vg, gg_ = v.to(DEV), g.to(DEV)
     w_nat = torch.empty_like(vg)
-    w_fwd, w_bwd = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    w_fwd, w_bwd = torch.full((n, ), float('nan'), device=DEV), torch.full((n, ), float('nan'), device=DEV)  # the call writes the padding
     L.check(L.lib().nfb_wn_pack_train(L.ptr(vg), L.ptr(gg_), L.ptr(w_nat), L.ptr(w_fwd), L.ptr(w_bwd), cout, cin, KK, 1e-5,
                                       L.stream()))
     GC.grad_close(w_nat, wd, 1e-6, 'weight norm')
