@@ -260,8 +260,11 @@ int nfb_bnflow_bwd(const float* gy, const float* x_in, const float* gldj, const 
                    const float* log_gamma, float* gx, float* g_log_gamma, float* g_beta, double* scratch, int B, int C,
                    int HW, nfb_stream_t stream);
 /* InvertibleConv1x1.forward (modules.py:470-482).  gz = W^T gy is nfb_invconv1x1_apply(gy, gz, NULL, NULL, W^T, ...);
- * gW[i,j] = sum_{b,p} gy[b,i,p] z[b,j,p] (C*C floats, zeroed by the call, fp32 atomics across position chunks). */
-int nfb_invconv1x1_wgrad(const float* gy, const float* z_in, float* gW, int B, int C, int HW, nfb_stream_t stream);
+ * gW[i,j] = sum_{b,p} gy[b,i,p] z[b,j,p] (C*C floats).  Position chunks store partial tiles in `scratch`
+ * (nfb_invconv1x1_wgrad_scratch floats, need not be zeroed) and a second kernel adds them: no atomics, deterministic. */
+long long nfb_invconv1x1_wgrad_scratch(int B, int C, int HW);
+int nfb_invconv1x1_wgrad(const float* gy, const float* z_in, float* gW, float* scratch, int B, int C, int HW,
+                         nfb_stream_t stream);
 /* chain rule through W = P (L o tril + I)(U o triu + diag(sign_s exp(log_s))) (modules.py:471-473) plus the log-det
  * term: gL, gU (C*C, zero outside the strict triangles), g_log_s (C). */
 int nfb_invconv1x1_weight_bwd(const float* gW, const float* P, const float* L, const float* U, const float* log_s,
@@ -287,12 +290,23 @@ int nfb_wn_pack_train(const float* v, const float* g, float* w_nat, float* w_fwd
 /* gradient of that map: gw (O, I*KK) -> gv (O, I*KK), gg (I*KK). */
 int nfb_wn_bwd(const float* v, const float* g, const float* gw, float* gv, float* gg, int O, int Ikk, float eps,
                nfb_stream_t stream);
+/* The same two maps for all n (<= 8) WeightNorm layers of one conditioner in ONE launch.  ptrs: HOST array of 5 device
+ * pointers per layer -- pack: (v, g, w_nat, w_fwd, w_bwd); backward: (v, g, gw, gv, gg); dims: HOST array of (O, I, KK)
+ * per layer. */
+int nfb_wn_pack_train_multi(const void* const* ptrs, const int* dims, int n, float eps, nfb_stream_t stream);
+int nfb_wn_bwd_multi(const void* const* ptrs, const int* dims, int n, float eps, nfb_stream_t stream);
 /* out (B, Cout, h, w) = conv_ks(in (B, Cin, h, w); packed w) + bias (+ skip); ks in {1, 3}, padding ks/2.  stats (device
  * double[2*Cout], may be NULL): per-channel sum and sum of squares of `out` for the BatchNorm that follows, accumulated
  * with fp64 atomics; zeroed by the call unless stats_zeroed != 0 (the caller carved it from one zero-filled arena).  The
  * data gradient of a layer is the same call with w_bwd and Cin / Cout exchanged. */
 int nfb_conv_train(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, double* stats,
                    int stats_zeroed, int B, int Cin, int Cout, int h, int w, int ks, nfb_stream_t stream);
+/* Data gradient of a layer fused with the BatchNorm+ReLU backward reduction of the layer below it:
+ * U (B, Cout, h, w) = conv_ks(gy (B, Cin, h, w); w_bwd) * [a > 0], sums = (sum U | sum U * xhat) -- what
+ * nfb_conv_train + nfb_bn_relu_bwd_reduce compute in two passes.  a / x: that BatchNorm's output (after ReLU) / input. */
+int nfb_conv_train_dgrad_bnrelu(const float* gy, const float* w_bwd, const float* a, const float* x, const float* mean_rstd,
+                                float* U, double* sums, int sums_zeroed, int B, int Cin, int Cout, int h, int w, int ks,
+                                nfb_stream_t stream);
 /* gw (Cout, Cin, ks, ks) = sum over batch and pixels of gy (B, Cout, h, w) x a (B, Cin, h, w); gb (Cout, may be NULL) =
  * sum of gy.  Sample groups write partial sums into `scratch` (nfb_conv_train_wgrad_scratch floats, need not be zeroed)
  * and a second kernel adds them up: no atomics, deterministic. */

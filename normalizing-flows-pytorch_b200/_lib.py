@@ -62,13 +62,17 @@ _SIGNATURES = {
     'nfb_rqs_coupling_bwd': [_P] * 6 + [_I] * 7 + [_F, _P],
     'nfb_actnorm_bwd': [_P] * 9 + [_I, _I, _I, _P],
     'nfb_bnflow_bwd': [_P] * 10 + [_I, _I, _I, _P],
-    'nfb_invconv1x1_wgrad': [_P, _P, _P, _I, _I, _I, _P],
+    'nfb_invconv1x1_wgrad': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'nfb_invconv1x1_wgrad_scratch': [_I, _I, _I],
     'nfb_invconv1x1_weight_bwd': [_P] * 10 + [_I, _I, _I, _P],
     'nfb_logit_bwd': [_P, _P, _P, _P, _F, _F, _I, _I, _P],
     'nfb_gauss_nll_bwd': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_wn_pack_train': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     'nfb_wn_bwd': [_P, _P, _P, _P, _P, _I, _I, _F, _P],
+    'nfb_wn_pack_train_multi': [_P, _P, _I, _F, _P],
+    'nfb_wn_bwd_multi': [_P, _P, _I, _F, _P],
     'nfb_conv_train': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_conv_train_dgrad_bnrelu': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_conv_train_wgrad': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nfb_conv_train_wgrad_scratch': [_I, _I, _I, _I, _I, _I],
     'nfb_bn_relu_fwd': [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P],
@@ -76,7 +80,7 @@ _SIGNATURES = {
     'nfb_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 _RESTYPES = {'nfb_error_string': ctypes.c_char_p, 'nfb_launch_count': ctypes.c_ulonglong,
-             'nfb_conv_train_wgrad_scratch': ctypes.c_longlong}
+             'nfb_conv_train_wgrad_scratch': ctypes.c_longlong, 'nfb_invconv1x1_wgrad_scratch': ctypes.c_longlong}
 
 _lib = None
 

@@ -355,46 +355,53 @@ static int launch_chan_bwd(const float* gy, const float* z, const float* gl, con
 //   W = P A U', A = L o tril(-1) + I, U' = U o triu(1) + diag(d), d = sign_s exp(log_s):
 //   M = P^T gW;  gL = (M U'^T) o tril(-1);  gU = (A^T M) o triu(1);  g_log_s = diag(A^T M) d + HW sum_b gl[b]
 // =====================================================================================================================
-constexpr int WG_T = 64;    // output tile (channels i x channels j) per CTA
-constexpr int WG_TP = 32;   // positions staged per step
-
-// CTA (256 threads) = one 64x64 tile of gW x one chunk of positions; thread = 4x4 outputs.  gy / z tiles are staged
-// position-major ([p][channel], padded) so each step is two 16-byte shared loads for 16 FMAs.
+// gW = GY (C x N) . Z^T (N x C), N = B*HW positions.  CTA = one T x T output tile x one chunk of positions; a thread
+// owns a 4 x 4 block of the tile, so (T/4)^2 threads cover it and the 256 threads form G = 256/(T/4)^2 groups that walk
+// disjoint positions of the staged chunk (T = 16: 16 groups -- the small channel counts C = 3, 12 still use every
+// thread); the groups are summed through shared memory, every CTA stores its partial tile with plain stores and
+// invconv_wgrad_reduce adds the chunks: no atomics, deterministic.
+template <int T>
 __global__ void __launch_bounds__(256) invconv_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ z,
-                                                           float* __restrict__ gW, int B, int C, int HW, int chunk) {
-    __shared__ __align__(16) float gs[WG_TP][WG_T + 4];
-    __shared__ __align__(16) float zs[WG_TP][WG_T + 4];
-    const int nt = (C + WG_T - 1) / WG_T;
+                                                           float* __restrict__ partial, int B, int C, int HW, int chunk) {
+    constexpr int TQ = T / 4;              // threads per tile side
+    constexpr int TG = TQ * TQ;            // threads per group
+    constexpr int G = 256 / TG;            // position groups
+    constexpr int TP = T == 64 ? 64 : 128; // positions staged per step
+    constexpr int LD = T + 4;              // padded row (positions-major tiles: [p][channel])
+    __shared__ __align__(16) float sm[2 * TP * LD];
+    float* gs = sm;
+    float* zs = sm + TP * LD;
+    const int nt = (C + T - 1) / T;
     const int ti = blockIdx.y / nt, tj = blockIdx.y - ti * nt;
-    const int i0 = ti * WG_T, j0 = tj * WG_T;
-    const int ti4 = (threadIdx.x >> 4) * 4, tj4 = (threadIdx.x & 15) * 4;
-    const long long npos = static_cast<long long>(B) * HW;
-    const long long q0 = static_cast<long long>(blockIdx.x) * chunk;
-    const long long q1 = q0 + chunk < npos ? q0 + chunk : npos;
+    const int i0 = ti * T, j0 = tj * T;
+    const int grp = threadIdx.x / TG, tl = threadIdx.x - grp * TG;
+    const int ti4 = (tl / TQ) * 4, tj4 = (tl % TQ) * 4;
+    const int npos = B * HW;
+    const int q0 = blockIdx.x * chunk;
+    const int q1 = q0 + chunk < npos ? q0 + chunk : npos;
     float acc[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
-    for (long long q = q0; q < q1; q += WG_TP) {
+    for (int q = q0; q < q1; q += TP) {
         __syncthreads();
-        // stage: element (ch, p) of both tiles; consecutive threads -> consecutive positions (coalesced for HW >= 32)
-        for (int idx = threadIdx.x; idx < WG_T * WG_TP; idx += blockDim.x) {
-            const int ch = idx / WG_TP, p = idx - ch * WG_TP;
-            const long long pos = q + p;
+        for (int idx = threadIdx.x; idx < T * TP; idx += 256) {  // consecutive threads -> consecutive positions
+            const int ch = idx / TP, p = idx - ch * TP;
+            const int pos = q + p;
             float a = 0.f, b = 0.f;
             if (pos < q1) {
-                const long long bb = pos / HW, pp = pos - bb * HW;
-                if (i0 + ch < C) a = __ldg(gy + (bb * C + i0 + ch) * HW + pp);
-                if (j0 + ch < C) b = __ldg(z + (bb * C + j0 + ch) * HW + pp);
+                const int bb = pos / HW, pp = pos - bb * HW;
+                if (i0 + ch < C) a = __ldg(gy + (static_cast<size_t>(bb) * C + i0 + ch) * HW + pp);
+                if (j0 + ch < C) b = __ldg(z + (static_cast<size_t>(bb) * C + j0 + ch) * HW + pp);
             }
-            gs[p][ch] = a;
-            zs[p][ch] = b;
+            gs[p * LD + ch] = a;
+            zs[p * LD + ch] = b;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int p = 0; p < WG_TP; ++p) {
-            const float4 a = ld4(&gs[p][ti4]), b = ld4(&zs[p][tj4]);
+#pragma unroll 4
+        for (int p = grp; p < TP; p += G) {
+            const float4 a = ld4(gs + p * LD + ti4), b = ld4(zs + p * LD + tj4);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -402,13 +409,37 @@ __global__ void __launch_bounds__(256) invconv_wgrad_kernel(const float* __restr
                 for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
         }
     }
+    // sum the G position groups through shared memory (reusing the staging tiles), then one store per tile entry
+    __syncthreads();
+    float* red = sm;  // G * T * T = 4096 floats, both staging tiles together hold at least that
+    static_assert(G * T * T <= 2 * TP * LD, "reduction buffer");
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int i = i0 + ti4 + u, j = j0 + tj4 + v;
-            if (i < C && j < C && acc[u][v] != 0.f) atomicAdd(gW + i * C + j, acc[u][v]);
-        }
+        for (int v = 0; v < 4; ++v) red[grp * T * T + (ti4 + u) * T + tj4 + v] = acc[u][v];
+    __syncthreads();
+    float* pw = partial + static_cast<size_t>(blockIdx.x) * C * C;
+    for (int e = threadIdx.x; e < T * T; e += 256) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < G; ++k) r += red[k * T * T + e];
+        const int i = i0 + e / T, j = j0 + e % T;
+        if (i < C && j < C) pw[i * C + j] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) invconv_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ gW, int n,
+                                                           int chunks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a0 = 0.f, a1 = 0.f;
+    int k = 0;
+    for (; k + 2 <= chunks; k += 2) {
+        a0 += __ldg(partial + static_cast<size_t>(k) * n + i);
+        a1 += __ldg(partial + static_cast<size_t>(k + 1) * n + i);
+    }
+    if (k < chunks) a0 += __ldg(partial + static_cast<size_t>(k) * n + i);
+    gW[i] = a0 + a1;
 }
 
 // one thread per (i, j): strictly-lower entries -> gL, strictly-upper -> gU, the diagonal -> g_log_s
@@ -809,22 +840,41 @@ extern "C" int nfb_bnflow_bwd(const float* gy, const float* x_in, const float* g
                                   stream);
 }
 
-extern "C" int nfb_invconv1x1_wgrad(const float* gy, const float* z_in, float* gW, int B, int C, int HW,
-                                    nfb_stream_t stream) {
-    if (!gy || !z_in || !gW) return NFB_ERR_NULL;
-    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
-    cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(gW, 0, sizeof(float) * C * C, st);
-    const int nt = (C + WG_T - 1) / WG_T;
+static void invconv_wgrad_plan(int B, int C, int HW, int& T, int& chunk, int& chunks) {
+    T = C <= 16 ? 16 : (C <= 32 ? 32 : 64);
+    const int nt = (C + T - 1) / T;
     const long long npos = static_cast<long long>(B) * HW;
-    // enough position chunks to fill the machine a few times over, each a multiple of the staging depth
-    long long chunks = (kSMs * 4 + nt * nt - 1) / (nt * nt);
-    long long chunk = (npos + chunks - 1) / chunks;
-    chunk = ((chunk + WG_TP - 1) / WG_TP) * WG_TP;
-    if (chunk < 4 * WG_TP) chunk = 4 * WG_TP;
-    chunks = (npos + chunk - 1) / chunk;
-    dim3 grid(static_cast<unsigned>(chunks), nt * nt);
-    invconv_wgrad_kernel<<<grid, 256, 0, st>>>(gy, z_in, gW, B, C, HW, static_cast<int>(chunk));
+    long long want = (kSMs * 2 + nt * nt - 1) / (nt * nt);   // about two CTAs per SM in total
+    long long ck = (npos + want - 1) / want;
+    ck = ((ck + 127) / 128) * 128;                           // whole staging steps
+    if (ck < 128) ck = 128;
+    chunk = static_cast<int>(ck);
+    chunks = static_cast<int>((npos + ck - 1) / ck);
+}
+
+extern "C" long long nfb_invconv1x1_wgrad_scratch(int B, int C, int HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    int T, chunk, chunks;
+    invconv_wgrad_plan(B, C, HW, T, chunk, chunks);
+    return static_cast<long long>(chunks) * C * C;
+}
+
+extern "C" int nfb_invconv1x1_wgrad(const float* gy, const float* z_in, float* gW, float* scratch, int B, int C, int HW,
+                                    nfb_stream_t stream) {
+    if (!gy || !z_in || !gW || !scratch) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
+    if (static_cast<long long>(B) * HW > (1LL << 30)) return NFB_ERR_SHAPE;
+    cudaStream_t st = as_stream(stream);
+    int T, chunk, chunks;
+    invconv_wgrad_plan(B, C, HW, T, chunk, chunks);
+    const int nt = (C + T - 1) / T;
+    dim3 grid(chunks, nt * nt);
+    if (T == 16) invconv_wgrad_kernel<16><<<grid, 256, 0, st>>>(gy, z_in, scratch, B, C, HW, chunk);
+    else if (T == 32) invconv_wgrad_kernel<32><<<grid, 256, 0, st>>>(gy, z_in, scratch, B, C, HW, chunk);
+    else invconv_wgrad_kernel<64><<<grid, 256, 0, st>>>(gy, z_in, scratch, B, C, HW, chunk);
+    const int rc = launch_status();
+    if (rc != NFB_OK) return rc;
+    invconv_wgrad_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(scratch, gW, C * C, chunks);
     return launch_status();
 }
 

@@ -23,9 +23,17 @@ namespace nfb {
 // block = 32 columns j (threadIdx.x) x 8 row slices (threadIdx.y: o = y, y+8, ...); the column norm is reduced through
 // shared memory.  Padding entries of the packed layouts (o >= O or i >= I inside a 32 x 32 chunk) are written as zeros,
 // so the caller needs no zero-fill.
-__global__ void __launch_bounds__(256) wn_pack_train_kernel(const float* __restrict__ v, const float* __restrict__ gw,
-                                                           float* __restrict__ w_nat, float* __restrict__ w_fwd,
-                                                           float* __restrict__ w_bwd, int O, int I, int KK, float eps) {
+constexpr int kMaxWnLayers = 8;
+struct WnLayer {
+    const float* v; const float* g; const float* gw;   // gw: weight gradient (backward only)
+    float* o0; float* o1; float* o2;                   // pack: w_nat, w_fwd, w_bwd;  backward: gv, gg, unused
+    int O, I, KK;
+};
+struct WnBatch { WnLayer l[kMaxWnLayers]; };
+
+__device__ __forceinline__ void wn_pack_body(const float* __restrict__ v, const float* __restrict__ gw,
+                                             float* __restrict__ w_nat, float* __restrict__ w_fwd,
+                                             float* __restrict__ w_bwd, int O, int I, int KK, float eps) {
     __shared__ float part[8][33];
     const int J = I * KK;
     const int n_ic = (I + 31) >> 5, n_oc = (O + 31) >> 5;
@@ -55,12 +63,22 @@ __global__ void __launch_bounds__(256) wn_pack_train_kernel(const float* __restr
         w_bwd[(static_cast<size_t>(i >> 5) * n_oc + (o >> 5)) * chunk + ((o & 31) * KK + (KK - 1 - tap)) * 32 + (i & 31)] = w;
     }
 }
+__global__ void __launch_bounds__(256) wn_pack_train_kernel(const float* __restrict__ v, const float* __restrict__ gw,
+                                                           float* __restrict__ w_nat, float* __restrict__ w_fwd,
+                                                           float* __restrict__ w_bwd, int O, int I, int KK, float eps) {
+    wn_pack_body(v, gw, w_nat, w_fwd, w_bwd, O, I, KK, eps);
+}
+__global__ void __launch_bounds__(256) wn_pack_train_multi_kernel(WnBatch bt, float eps) {
+    const WnLayer& l = bt.l[blockIdx.y];
+    if (blockIdx.x * 32 >= ((l.I + 31) >> 5) * 32 * l.KK) return;  // block-uniform: this layer has fewer columns
+    wn_pack_body(l.v, l.g, l.o0, l.o1, l.o2, l.O, l.I, l.KK, eps);
+}
 
 // gradient of the WeightNorm map: s_j = g_j / (n_j + eps), n_j = ||v[:, j]||, d_j = sum_o gw[o,j] v[o,j]
 //   gg_j = d_j / (n_j + eps);   gv[o,j] = gw[o,j] s_j - v[o,j] d_j g_j / ((n_j + eps)^2 n_j)
-__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                                    const float* __restrict__ gw, float* __restrict__ gv,
-                                                    float* __restrict__ gg, int O, int J, float eps) {
+__device__ __forceinline__ void wn_bwd_body(const float* __restrict__ v, const float* __restrict__ g,
+                                            const float* __restrict__ gw, float* __restrict__ gv, float* __restrict__ gg,
+                                            int O, int J, float eps) {
     __shared__ float p_ss[8][33], p_d[8][33];
     const int j = blockIdx.x * 32 + threadIdx.x;
     const int ty = threadIdx.y;
@@ -87,6 +105,16 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ v
         gv[k] = fmaf(__ldg(gw + k), sc, -__ldg(v + k) * c);
     }
 }
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                    const float* __restrict__ gw, float* __restrict__ gv,
+                                                    float* __restrict__ gg, int O, int J, float eps) {
+    wn_bwd_body(v, g, gw, gv, gg, O, J, eps);
+}
+__global__ void __launch_bounds__(256) wn_bwd_multi_kernel(WnBatch bt, float eps) {
+    const WnLayer& l = bt.l[blockIdx.y];
+    if (blockIdx.x * 32 >= l.I * l.KK) return;
+    wn_bwd_body(l.v, l.g, l.gw, l.o0, l.o1, l.O, l.I * l.KK, eps);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // convolution layer (forward, and data gradient with w_bwd): out = conv_KS(in; w) + bias (+ skip), optional per-channel
@@ -100,6 +128,11 @@ struct ConvArgs {
     float* out;          // (B, Cout, H, W)
     double* stats;       // [2*Cout] (sum | sum of squares), accumulated; or null
     int Cin, Cout, B;
+    // data-gradient mode (mask_a != null): the BatchNorm+ReLU backward reduction is fused into the epilogue --
+    // out = U = conv * [mask_a > 0], stats = (sum U | sum U * xhat) with xhat = (mask_x - mean) * rstd
+    const float* mask_a;
+    const float* mask_x;
+    const float* mean_rstd;
 };
 
 template <int H, int W, int NT, int OCT, int KS>
@@ -178,9 +211,17 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
                     const float4 k = ldg4(A.skip + off);
                     v.x += k.x; v.y += k.y; v.z += k.z; v.w += k.w;
                 }
+                if (A.mask_a) {
+                    const float4 a4 = ldg4(A.mask_a + off), x4 = ldg4(A.mask_x + off);
+                    const float m = __ldg(A.mean_rstd + ch), rs = __ldg(A.mean_rstd + A.Cout + ch);
+                    v.x = a4.x > 0.f ? v.x : 0.f; v.y = a4.y > 0.f ? v.y : 0.f;
+                    v.z = a4.z > 0.f ? v.z : 0.f; v.w = a4.w > 0.f ? v.w : 0.f;
+                    s2 = fmaf(v.x, (x4.x - m) * rs, fmaf(v.y, (x4.y - m) * rs, fmaf(v.z, (x4.z - m) * rs, v.w * ((x4.w - m) * rs))));
+                } else {
+                    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                }
                 st4(A.out + off, v);
                 s1 = (v.x + v.y) + (v.z + v.w);
-                s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
             }
             if (A.stats) {  // uniform branch
 #pragma unroll
@@ -226,16 +267,18 @@ __device__ __forceinline__ void load_row(float (&dst)[W], const float* __restric
     }
 }
 
-template <int H, int W, int KS>
+// SPI samples are staged per iteration (16 image rows in every configuration: 1 x 16, 4 x 8 or 8 x 4), so the small
+// feature maps do not pay two block barriers per 16 pixels.
+template <int H, int W, int KS, int SPI>
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ a,
                                                    float* __restrict__ partial, int Cin, int Cout, int B, int spc) {
     constexpr int KK = KS * KS;
-    constexpr int GS = H * W + 4;          // channel stride of the gy tile  (stride/4 odd: conflict-free float4 reads)
-    constexpr int AS = (H + 2) * W + 4;    // channel stride of the a tile (zero rows above / below)
+    constexpr int GS = SPI * H * W + 4;          // channel stride of the gy tile (stride/4 odd: conflict-free float4 reads)
+    constexpr int AS = SPI * (H + 2) * W + 4;    // channel stride of the a tile (zero rows above / below every sample)
     static_assert(((GS / 4) & 1) == 1 && ((AS / 4) & 1) == 1, "padded strides");
     extern __shared__ __align__(16) float wg_smem[];
-    float* gys = wg_smem;            // [32][GS]
-    float* as = wg_smem + 32 * GS;   // [32][AS]
+    float* gys = wg_smem;            // [32][SPI][H*W]
+    float* as = wg_smem + 32 * GS;   // [32][SPI][(H+2)*W]
     const int n_ic = (Cin + 31) >> 5;
     const int oc = blockIdx.y / n_ic, ic = blockIdx.y - oc * n_ic;
     const int t = threadIdx.x;
@@ -252,22 +295,28 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy
     constexpr int HWv = H * W / 4;
     const int b0 = blockIdx.x * spc;
     const int b1 = (b0 + spc) < B ? (b0 + spc) : B;
-    for (int b = b0; b < b1; ++b) {
+    for (int b = b0; b < b1; b += SPI) {
         __syncthreads();
-        for (int i = t; i < 32 * HWv; i += 256) {
-            const int ch = i / HWv, rem = i - ch * HWv;
+        for (int i = t; i < 32 * SPI * HWv; i += 256) {
+            const int ch = i / (SPI * HWv);
+            int rem = i - ch * (SPI * HWv);
+            const int sp = rem / HWv;
+            rem -= sp * HWv;
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = g4;
-            if (oc * 32 + ch < Cout) g4 = ldg4(gy + (static_cast<size_t>(b) * Cout + oc * 32 + ch) * (H * W) + 4 * rem);
-            if (ic * 32 + ch < Cin) a4 = ldg4(a + (static_cast<size_t>(b) * Cin + ic * 32 + ch) * (H * W) + 4 * rem);
-            st4(gys + ch * GS + 4 * rem, g4);
-            st4(as + ch * AS + W + 4 * rem, a4);
+            if (b + sp < b1) {
+                if (oc * 32 + ch < Cout) g4 = ldg4(gy + (static_cast<size_t>(b + sp) * Cout + oc * 32 + ch) * (H * W) + 4 * rem);
+                if (ic * 32 + ch < Cin) a4 = ldg4(a + (static_cast<size_t>(b + sp) * Cin + ic * 32 + ch) * (H * W) + 4 * rem);
+            }
+            st4(gys + ch * GS + sp * (H * W) + 4 * rem, g4);
+            st4(as + ch * AS + sp * ((H + 2) * W) + W + 4 * rem, a4);
         }
         __syncthreads();
 #pragma unroll 1
-        for (int y = 0; y < H; ++y) {
+        for (int r = 0; r < SPI * H; ++r) {
+            const int sp = r / H, y = r - sp * H;
             float gr[2][W];
-            load_row<W>(gr[0], gys + op * GS + y * W);
-            load_row<W>(gr[1], gys + (op + 16) * GS + y * W);
+            load_row<W>(gr[0], gys + op * GS + sp * (H * W) + y * W);
+            load_row<W>(gr[1], gys + (op + 16) * GS + sp * (H * W) + y * W);
             if (cp == 0) {
 #pragma unroll
                 for (int x = 0; x < W; ++x) { gbacc[0] += gr[0][x]; gbacc[1] += gr[1][x]; }
@@ -276,8 +325,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy
             for (int dy = 0; dy < KS; ++dy) {
                 float ar[2][W];
                 const int row = KS == 3 ? y + dy : y + 1;  // padded row index (row 0 = zeros above the image)
-                load_row<W>(ar[0], as + cp * AS + row * W);
-                load_row<W>(ar[1], as + (cp + 16) * AS + row * W);
+                load_row<W>(ar[0], as + cp * AS + sp * ((H + 2) * W) + row * W);
+                load_row<W>(ar[1], as + (cp + 16) * AS + sp * ((H + 2) * W) + row * W);
 #pragma unroll
                 for (int dx = 0; dx < KS; ++dx) {
                     const int sh = KS == 3 ? dx - 1 : 0;
@@ -471,12 +520,63 @@ extern "C" int nfb_wn_pack_train(const float* v, const float* g, float* w_nat, f
     return launch_status();
 }
 
+// all WeightNorm layers of one conditioner in one launch.  ptrs: HOST array of 5 device pointers per layer
+// (pack: v, g, w_nat, w_fwd, w_bwd; backward: v, g, gw, gv, gg); dims: HOST array of (O, I, KK) per layer.
+static int wn_multi(const void* const* ptrs, const int* dims, int n, float eps, bool backward, nfb_stream_t stream) {
+    if (!ptrs || !dims) return NFB_ERR_NULL;
+    if (n <= 0 || n > kMaxWnLayers) return NFB_ERR_SHAPE;
+    WnBatch bt;
+    int max_cols = 0;
+    for (int i = 0; i < n; ++i) {
+        WnLayer& l = bt.l[i];
+        for (int k = 0; k < 5; ++k)
+            if (!ptrs[5 * i + k]) return NFB_ERR_NULL;
+        l.O = dims[3 * i]; l.I = dims[3 * i + 1]; l.KK = dims[3 * i + 2];
+        if (l.O <= 0 || l.I <= 0 || (l.KK != 1 && l.KK != 9)) return NFB_ERR_SHAPE;
+        l.v = static_cast<const float*>(ptrs[5 * i]);
+        l.g = static_cast<const float*>(ptrs[5 * i + 1]);
+        if (!backward) {
+            l.gw = nullptr;
+            l.o0 = static_cast<float*>(const_cast<void*>(ptrs[5 * i + 2]));
+            l.o1 = static_cast<float*>(const_cast<void*>(ptrs[5 * i + 3]));
+            l.o2 = static_cast<float*>(const_cast<void*>(ptrs[5 * i + 4]));
+        } else {
+            l.gw = static_cast<const float*>(ptrs[5 * i + 2]);
+            l.o0 = static_cast<float*>(const_cast<void*>(ptrs[5 * i + 3]));
+            l.o1 = static_cast<float*>(const_cast<void*>(ptrs[5 * i + 4]));
+            l.o2 = nullptr;
+        }
+        const int cols = backward ? l.I * l.KK : ((l.I + 31) / 32) * 32 * l.KK;
+        if (cols > max_cols) max_cols = cols;
+    }
+    dim3 grid((max_cols + 31) / 32, n);
+    if (backward) wn_bwd_multi_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(bt, eps);
+    else wn_pack_train_multi_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(bt, eps);
+    return launch_status();
+}
+extern "C" int nfb_wn_pack_train_multi(const void* const* ptrs, const int* dims, int n, float eps, nfb_stream_t stream) {
+    return wn_multi(ptrs, dims, n, eps, false, stream);
+}
+extern "C" int nfb_wn_bwd_multi(const void* const* ptrs, const int* dims, int n, float eps, nfb_stream_t stream) {
+    return wn_multi(ptrs, dims, n, eps, true, stream);
+}
+
 extern "C" int nfb_wn_bwd(const float* v, const float* g, const float* gw, float* gv, float* gg, int O, int Ikk, float eps,
                           nfb_stream_t stream) {
     if (!v || !g || !gw || !gv || !gg) return NFB_ERR_NULL;
     if (O <= 0 || Ikk <= 0) return NFB_ERR_SHAPE;
     wn_bwd_kernel<<<(Ikk + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(v, g, gw, gv, gg, O, Ikk, eps);
     return launch_status();
+}
+
+static int conv_dispatch(const ConvArgs& A, int h, int w, int ks, cudaStream_t st) {
+#define NFB_CL(H_, W_, NT_, OCT_)                                                     \
+    return ks == 3 ? launch_conv_layer<H_, W_, NT_, OCT_, 3>(A, st) : launch_conv_layer<H_, W_, NT_, OCT_, 1>(A, st)
+    if (h == 16 && w == 16) { NFB_CL(16, 16, 256, 8); }
+    if (h == 8 && w == 8) { NFB_CL(8, 8, 128, 4); }
+    if (h == 4 && w == 4) { NFB_CL(4, 4, 128, 2); }
+#undef NFB_CL
+    return NFB_ERR_UNSUPPORTED;
 }
 
 extern "C" int nfb_conv_train(const float* in, const float* w_packed, const float* bias, const float* skip, float* out,
@@ -487,20 +587,26 @@ extern "C" int nfb_conv_train(const float* in, const float* w_packed, const floa
     if (!aligned16(in) || !aligned16(out) || !aligned16(w_packed) || (skip && !aligned16(skip))) return NFB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     if (stats && !stats_zeroed) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, st);
-    const ConvArgs A{in, w_packed, bias, skip, out, stats, Cin, Cout, B};
-#define NFB_CL(H_, W_, NT_, OCT_)                                                     \
-    return ks == 3 ? launch_conv_layer<H_, W_, NT_, OCT_, 3>(A, st) : launch_conv_layer<H_, W_, NT_, OCT_, 1>(A, st)
-    if (h == 16 && w == 16) { NFB_CL(16, 16, 256, 8); }
-    if (h == 8 && w == 8) { NFB_CL(8, 8, 128, 4); }
-    if (h == 4 && w == 4) { NFB_CL(4, 4, 128, 2); }
-#undef NFB_CL
-    return NFB_ERR_UNSUPPORTED;
+    const ConvArgs A{in, w_packed, bias, skip, out, stats, Cin, Cout, B, nullptr, nullptr, nullptr};
+    return conv_dispatch(A, h, w, ks, st);
+}
+
+extern "C" int nfb_conv_train_dgrad_bnrelu(const float* gy, const float* w_bwd, const float* a, const float* x,
+                                           const float* mean_rstd, float* U, double* sums, int sums_zeroed, int B, int Cin,
+                                           int Cout, int h, int w, int ks, nfb_stream_t stream) {
+    if (!gy || !w_bwd || !a || !x || !mean_rstd || !U || !sums) return NFB_ERR_NULL;
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || (ks != 1 && ks != 3)) return NFB_ERR_SHAPE;
+    if (!aligned16(gy) || !aligned16(w_bwd) || !aligned16(a) || !aligned16(x) || !aligned16(U)) return NFB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (!sums_zeroed) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cout, st);
+    const ConvArgs A{gy, w_bwd, nullptr, nullptr, U, sums, Cin, Cout, B, a, x, mean_rstd};
+    return conv_dispatch(A, h, w, ks, st);
 }
 
 // samples per CTA: large enough that the partial-sum traffic (groups x |gw|) stays small next to the FMA work
 static int wgrad_spc(int B, int Cin, int Cout, int h, int w) {
     const int pairs = ((Cin + 31) / 32) * ((Cout + 31) / 32);
-    int spc = h * w >= 256 ? 2 : (h * w >= 64 ? 4 : 16);
+    int spc = h * w >= 256 ? 2 : (h * w >= 64 ? 4 : 8);  // = a multiple of the samples staged per iteration
     const int fill = (B * pairs + kSMs * 2 - 1) / (kSMs * 2);  // never more than about two CTAs per SM in total
     if (spc < fill) spc = fill;
     if (spc > B) spc = B;
@@ -525,22 +631,22 @@ extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, 
     const int groups = (B + spc - 1) / spc;
     dim3 grid(groups, pairs);
     int rc = NFB_ERR_UNSUPPORTED;
-#define NFB_WG(H_, W_)                                                                                       \
+#define NFB_WG(H_, W_, SPI_)                                                                                 \
     do {                                                                                                     \
-        constexpr size_t smem = sizeof(float) * 32 * ((H_) * (W_) + 4 + ((H_) + 2) * (W_) + 4);             \
+        constexpr size_t smem = sizeof(float) * 32 * ((SPI_) * (H_) * (W_) + 4 + (SPI_) * ((H_) + 2) * (W_) + 4); \
         static bool attr_set = false;                                                                        \
         if (!attr_set) {                                                                                     \
-            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3, SPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1, SPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
             attr_set = true;                                                                                 \
         }                                                                                                    \
-        if (ks == 3) wgrad_kernel<H_, W_, 3><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);    \
-        else wgrad_kernel<H_, W_, 1><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);            \
+        if (ks == 3) wgrad_kernel<H_, W_, 3, SPI_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc); \
+        else wgrad_kernel<H_, W_, 1, SPI_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);      \
         rc = launch_status();                                                                                \
     } while (0)
-    if (h == 16 && w == 16) NFB_WG(16, 16);
-    else if (h == 8 && w == 8) NFB_WG(8, 8);
-    else if (h == 4 && w == 4) NFB_WG(4, 4);
+    if (h == 16 && w == 16) NFB_WG(16, 16, 1);
+    else if (h == 8 && w == 8) NFB_WG(8, 8, 4);
+    else if (h == 4 && w == 4) NFB_WG(4, 4, 8);
 #undef NFB_WG
     if (rc != NFB_OK) return rc;
     const int n_w = Cout * Cin * ks * ks;

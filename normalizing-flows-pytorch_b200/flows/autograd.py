@@ -223,7 +223,8 @@ class InvConv1x1Fn(Function):
         L.check(L.lib().nfb_invconv1x1_apply(L.ptr(gy), L.ptr(gz), None, None, L.ptr(Wt), None, 0.0, B, C, HW,
                                              L.stream()))
         gW = torch.empty_like(Wm)
-        L.check(L.lib().nfb_invconv1x1_wgrad(L.ptr(gy), L.ptr(z), L.ptr(gW), B, C, HW, L.stream()))
+        scratch = torch.empty(int(L.lib().nfb_invconv1x1_wgrad_scratch(B, C, HW)), device=z.device, dtype=torch.float32)
+        L.check(L.lib().nfb_invconv1x1_wgrad(L.ptr(gy), L.ptr(z), L.ptr(gW), L.ptr(scratch), B, C, HW, L.stream()))
         gL, gU, gls = torch.empty_like(Lp), torch.empty_like(Up), torch.empty_like(log_s)
         L.check(L.lib().nfb_invconv1x1_weight_bwd(L.ptr(gW), L.ptr(P), L.ptr(Lp), L.ptr(Up), L.ptr(log_s), L.ptr(sign_s),
                                                   L.ptr(gl), L.ptr(gL), L.ptr(gU), L.ptr(gls), B, C, HW, L.stream()))

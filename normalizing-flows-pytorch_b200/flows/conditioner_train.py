@@ -11,6 +11,8 @@ activation is kept for the backward pass (11 tensors of (B, 32, h, w) per condit
   5 x (weight, bias)               of mid_block.{0,1}.net.{0,3}, out_block.0 (BatchNorm gamma / beta) (differentiable)
   5 x (running_mean, running_var)  of the same BatchNorms                                      (updated in place)
 """
+import ctypes
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -73,6 +75,21 @@ def _bn_relu_bwd(ga, a, x, mr, gamma, add, sums=None):
     return gx, gg, gb
 
 
+def _dgrad_bn_relu(gy, w_bwd, cin, ks, a, x, mr, gamma, add, sums):
+    """Data gradient of a layer (C_in = cin channels of gy -> 32) fused with the ReLU mask and the two BatchNorm sums of
+    the layer below, then the BatchNorm input gradient (+ residual branch) -> (gx, g_gamma, g_beta)."""
+    B, C, h, w = x.shape
+    U = torch.empty_like(x)
+    L.check(L.lib().nfb_conv_train_dgrad_bnrelu(L.ptr(gy), L.ptr(w_bwd), L.ptr(a), L.ptr(x), L.ptr(mr), L.ptr(U),
+                                                sums.data_ptr(), 1, B, cin, C, h, w, ks, L.stream()))
+    gx = torch.empty_like(x)
+    gg, gb = torch.empty_like(gamma), torch.empty_like(gamma)
+    L.check(L.lib().nfb_bn_bwd_apply(L.ptr(U), L.ptr(x), L.ptr(mr), L.ptr(gamma), sums.data_ptr(),
+                                     L.ptr(add) if add is not None else None, L.ptr(gx), L.ptr(gg), L.ptr(gb), B, C, h * w,
+                                     L.stream()))
+    return gx, gg, gb
+
+
 class ConvNetTrainFn(Function):
 
     @staticmethod
@@ -81,17 +98,20 @@ class ConvNetTrainFn(Function):
         wn, bn, rs = T[:18], T[18:28], T[28:38]
         wn_eps, bn_eps, momentum = cfg
         cin, cout = wn[0].size(1), wn[15].size(0)
-        packed = []
-        for i in range(6):
+        packed, ptrs, dims, keep = [], [], [], []
+        for i in range(6):  # WeightNorm + packing of all six layers: one launch
             v, g = wn[3 * i], wn[3 * i + 1]
             O, I, KK = v.size(0), v.size(1), v[0, 0].numel()
             n = ((O + 31) // 32) * ((I + 31) // 32) * 32 * KK * 32
             w_nat = torch.empty_like(v)
             w_fwd = torch.empty(n, device=v.device, dtype=torch.float32)  # padding is written by the kernel
             w_bwd = torch.empty(n, device=v.device, dtype=torch.float32)
-            L.check(L.lib().nfb_wn_pack_train(L.ptr(v), L.ptr(g), L.ptr(w_nat), L.ptr(w_fwd), L.ptr(w_bwd), O, I, KK,
-                                              float(wn_eps), L.stream()))
+            ptrs += [L.ptr(v), L.ptr(g), L.ptr(w_nat), L.ptr(w_fwd), L.ptr(w_bwd)]
+            dims += [O, I, KK]
+            keep.append(w_nat)
             packed.append((w_fwd, w_bwd))
+        L.check(L.lib().nfb_wn_pack_train_multi((ctypes.c_void_p * 30)(*ptrs), (ctypes.c_int * 18)(*dims), 6,
+                                                float(wn_eps), L.stream()))
         b = [wn[3 * i + 2] for i in range(6)]
         gam, bet = [bn[2 * i] for i in range(5)], [bn[2 * i + 1] for i in range(5)]
 
@@ -128,30 +148,28 @@ class ConvNetTrainFn(Function):
         gw, gb, ggam, gbet = [None] * 6, [None] * 6, [None] * 5, [None] * 5
         # out block
         gw[5], gb[5] = _wgrad(gout, a5, F32, cout, 1)
-        ga, _ = _conv(gout, wb[5], None, None, cout, F32, 1, False)
         arena = torch.zeros(5 * 2 * F32, device=gout.device, dtype=torch.float64)  # the five BatchNorm-backward sum pairs
         acc = [arena[i * 2 * F32:(i + 1) * 2 * F32] for i in range(5)]
-        G, ggam[4], gbet[4] = _bn_relu_bwd(ga, a5, h2, mr5, gam[4], None, acc[4])
+        G, ggam[4], gbet[4] = _dgrad_bn_relu(gout, wb[5], cout, 1, a5, h2, mr5, gam[4], None, acc[4])
         # residual blocks, last first: (layer indices, BatchNorm indices, activations)
         for (l2, l1, bB, bA, aB, yB, mrB, aA, hA, mrA) in ((4, 3, 3, 2, a4, y2, mr4, a3, h1, mr3),
                                                           (2, 1, 1, 0, a2, y1, mr2, a1, h0, mr1)):
             gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, 3)
-            ga, _ = _conv(G, wb[l2], None, None, F32, F32, 3, False)
-            gy, ggam[bB], gbet[bB] = _bn_relu_bwd(ga, aB, yB, mrB, gam[bB], None, acc[bB])
+            gy, ggam[bB], gbet[bB] = _dgrad_bn_relu(G, wb[l2], F32, 3, aB, yB, mrB, gam[bB], None, acc[bB])
             gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, 3)
-            ga, _ = _conv(gy, wb[l1], None, None, F32, F32, 3, False)
-            G, ggam[bA], gbet[bA] = _bn_relu_bwd(ga, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
+            G, ggam[bA], gbet[bA] = _dgrad_bn_relu(gy, wb[l1], F32, 3, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
         gw[0], gb[0] = _wgrad(G, x, cin, F32, 3)
         gx = None
         if ctx.needs_input_grad[0]:
             gx, _ = _conv(G, wb[0], None, None, F32, cin, 3, False)
-        grads = []
-        for i in range(6):
+        grads, ptrs, dims = [], [], []
+        for i in range(6):  # WeightNorm backward of all six layers: one launch
             v, g = vs[i], gs[i]
             gv, gg = torch.empty_like(v), torch.empty_like(g)
-            L.check(L.lib().nfb_wn_bwd(L.ptr(v), L.ptr(g), L.ptr(gw[i]), L.ptr(gv), L.ptr(gg), v.size(0), v[0].numel(),
-                                       wn_eps, L.stream()))
+            ptrs += [L.ptr(v), L.ptr(g), L.ptr(gw[i]), L.ptr(gv), L.ptr(gg)]
+            dims += [v.size(0), v.size(1), v[0, 0].numel()]
             grads += [gv, gg, gb[i]]
+        L.check(L.lib().nfb_wn_bwd_multi((ctypes.c_void_p * 30)(*ptrs), (ctypes.c_int * 18)(*dims), 6, wn_eps, L.stream()))
         for i in range(5):
             grads += [ggam[i], gbet[i]]
         return (gx, None) + tuple(grads) + (None, ) * 10

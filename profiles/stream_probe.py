@@ -100,8 +100,9 @@ cases.append(('actnorm BWD 3x32x32', lambda: L.check(L.lib().nfb_actnorm_bwd(
 z48 = z.view(B, 48, 8, 8)
 W48 = torch.randn(48, 48, device='cuda') / 7
 gW = torch.empty(48, 48, device='cuda')
+wscr = torch.empty(int(L.lib().nfb_invconv1x1_wgrad_scratch(B, 48, 64)), device='cuda')
 cases.append(('invconv wgrad C=48 8x8', lambda: L.check(L.lib().nfb_invconv1x1_wgrad(
-    gy.data_ptr(), z48.data_ptr(), gW.data_ptr(), B, 48, 64, st)), 8 * D))
+    gy.data_ptr(), z48.data_ptr(), gW.data_ptr(), wscr.data_ptr(), B, 48, 64, st)), 8 * D))
 cases.append(('invconv apply (W^T gy) C=48 8x8', lambda: L.check(L.lib().nfb_invconv1x1_apply(
     gy.data_ptr(), gz.data_ptr(), None, None, W48.data_ptr(), None, 0.0, B, 48, 64, st)), 8 * D))
 gym = torch.randn_like(zm)

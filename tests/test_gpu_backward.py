@@ -384,7 +384,7 @@ def test_native_train_conditioner_vs_library(cin, cout, hw, B):
         out = net(xx)
         (out * R).sum().backward()
         launches = nfb()._lib.launch_count() - n0
-        assert (launches > 40) == native, launches  # the native path really is made of libnfb200 launches
+        assert (launches >= 20) == native, launches  # the native path really is made of libnfb200 launches
         res.append((out.detach(), xx.grad, {k: p.grad.clone() for k, p in net.named_parameters()},
                     {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k}))
     (o1, g1, p1, s1), (o0, g0, p0, s0) = res
@@ -435,3 +435,30 @@ def test_train_conv_kernels_vs_torch(cin, cout, hw, ks, B):
     gw, gb = CT._wgrad(gy.to(DEV), x.to(DEV), cin, cout, ks)
     GC.grad_close(gw, wd.grad, 1e-5, 'weight gradient')
     GC.grad_close(gb, gy.double().sum(dim=(0, 2, 3)), 1e-5, 'bias gradient')
+
+
+@pytest.mark.parametrize('hw,B', [(16, 5), (8, 9), (4, 33)])
+def test_bn_relu_kernels_vs_torch(hw, B):
+    """bn_relu_fwd (+ running statistics) and the two-pass BatchNorm+ReLU backward against torch autograd in fp64."""
+    import torch.nn.functional as TF
+    nfb()
+    from nfb200.flows import conditioner_train as CT
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 32, hw, hw, generator=gen) * 1.5 + 0.3
+    gamma, beta = torch.rand(32, generator=gen) + 0.5, torch.randn(32, generator=gen) * 0.2
+    ga, add = torch.randn(B, 32, hw, hw, generator=gen), torch.randn(B, 32, hw, hw, generator=gen)
+    xd, gd, bd = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm, rv = torch.zeros(32, dtype=torch.float64), torch.ones(32, dtype=torch.float64)
+    ad = torch.relu(TF.batch_norm(xd, rm, rv, gd, bd, True, 0.1, 1e-5))
+    (ad * ga.double()).sum().backward()
+    xg = x.to(DEV)
+    stats = torch.stack([xg.double().sum(dim=(0, 2, 3)), (xg.double() ** 2).sum(dim=(0, 2, 3))]).reshape(-1).contiguous()
+    rmg, rvg = torch.zeros(32, device=DEV), torch.ones(32, device=DEV)
+    a, mr = CT._bn_relu(xg, stats, gamma.to(DEV), beta.to(DEV), rmg, rvg, 0.1, 1e-5)
+    GC.grad_close(a, ad, 2e-6, 'bn_relu forward')
+    GC.grad_close(rmg, rm, 1e-6, 'running_mean')
+    GC.grad_close(rvg, rv, 1e-6, 'running_var')
+    gx, gg, gb = CT._bn_relu_bwd(ga.to(DEV), a, xg, mr, gamma.to(DEV), add.to(DEV))
+    GC.grad_close(gx, xd.grad + add.double(), 1e-5, 'gx')
+    GC.grad_close(gg, gd.grad, 1e-5, 'g gamma')
+    GC.grad_close(gb, bd.grad, 1e-5, 'g beta')
