@@ -305,7 +305,7 @@ def train_probe(net, dev_ring, batch, world, steps):
     import nfb200
     from nfb200 import parallel
     out = {'unit': 'samples/s',
-           'note': 'train-mode fwd + gradient kernels + flat-bucket all-reduce + Adam; conditioner fwd/bwd on cuDNN'}
+           'note': 'train-mode fwd + gradient kernels (bijections and ConvNet conditioner) + flat-bucket all-reduce + Adam'}
     ring = len(dev_ring)
     # eager
     tnet = copy.deepcopy(net).train()
