@@ -282,6 +282,7 @@ def test_channel_layers_and_invconv_bwd_vs_oracle_fp64(shape):
     dict(kind='RealNVP', dims=(64, ), datatype=None, layers=4, B=256, coupling='rqs'),   # BASELINE cfg 4 bijection
     dict(kind='RealNVP', dims=(2, ), datatype=None, layers=6, B=512),
     dict(kind='Flowpp', dims=(3, 16, 16), datatype='image', layers=1, B=4, mixtures=4),
+    dict(kind='Glow', dims=(1, 32, 32), datatype='image', layers=1, B=6),   # padded MNIST shape (dataset.py:67-72): C = 1
 ])
 def test_training_step_gradients_vs_oracle(cfg):
     """Whole training step (train mode, loss of main.py:85) against CPU autograd through the oracle in fp32."""

@@ -201,6 +201,7 @@ def perturb_(net, seed=0):
     dict(model='realnvp', dims=(64, ), datatype=None, layers=8, B=4096),      # cfg 4 proxy (affine)
     dict(model='realnvp', dims=(2, ), datatype=None, layers=6, B=512),        # cfg 1
     dict(model='flowpp', dims=(3, 32, 32), datatype='image', layers=1, B=2, mixtures=8),  # cfg 3 stack at K=1
+    dict(model='glow', dims=(1, 32, 32), datatype='image', layers=2, B=4),   # the reference's padded MNIST (dataset.py:67-72): C = 1
 ])
 def test_model_vs_oracle(cfg):
     n = nfb()
