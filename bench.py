@@ -600,7 +600,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='nfb200', choices=['nfb200', 'reference'])
     ap.add_argument('--workload', default='glow32', choices=sorted(WORKLOADS))
-    ap.add_argument('--streams', type=int, default=3, help='batches in flight (one CUDA graph + stream each)')
+    ap.add_argument('--streams', type=int, default=5, help='batches in flight (one CUDA graph + stream each)')
     ap.add_argument('--train', action='store_true', help='also time the training step when N > 1 (default: N = 1 only)')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step probe')
     args = ap.parse_args()

@@ -326,6 +326,11 @@ int nfb_bn_relu_bwd_reduce(const float* ga, const float* a, const float* x, cons
 int nfb_bn_bwd_apply(const float* U, const float* x, const float* mean_rstd, const float* gamma, const double* sums,
                      const float* add, float* gx, float* g_gamma, float* g_beta, int B, int C, int HW, nfb_stream_t stream);
 
+/* (B, C) rows <-> (B/HW, C, HW) channel planes (B % HW == 0): the train-mode MLP conditioner (modules.py:391-413) runs on
+ * the convolution-layer kernels above as six 1x1 convolutions over planes of HW rows each. */
+int nfb_rows_to_planes(const float* rows, float* planes, int B, int C, int HW, nfb_stream_t stream);
+int nfb_planes_to_rows(const float* planes, float* rows, int B, int C, int HW, nfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

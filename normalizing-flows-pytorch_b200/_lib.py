@@ -69,6 +69,8 @@ _SIGNATURES = {
     'nfb_gauss_nll_bwd': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_wn_pack_train': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     'nfb_wn_bwd': [_P, _P, _P, _P, _P, _I, _I, _F, _P],
+    'nfb_rows_to_planes': [_P, _P, _I, _I, _I, _P],
+    'nfb_planes_to_rows': [_P, _P, _I, _I, _I, _P],
     'nfb_wn_pack_train_multi': [_P, _P, _I, _F, _P],
     'nfb_wn_bwd_multi': [_P, _P, _I, _F, _P],
     'nfb_conv_train': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

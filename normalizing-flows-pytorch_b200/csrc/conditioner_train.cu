@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
 #pragma unroll
         for (int o = 0; o < OCT; ++o) {
             const int ch = oc * 32 + og * OCT + o;
-            float s1 = 0.f, s2 = 0.f;
+            // moments in fp64 from the start: var = E[x^2] - mean^2 cancels when |mean| >> std (a bias in front of a
+            // BatchNorm), and fp32 squares would leave the variance with ~1e-5 relative error
+            double s1 = 0.0, s2 = 0.0;
             if (valid && ch < A.Cout) {
                 const float bias = A.bias ? __ldg(A.bias + ch) : 0.f;
                 float4 v = make_float4(acc[o][0] + bias, acc[o][1] + bias, acc[o][2] + bias, acc[o][3] + bias);
@@ -216,12 +218,14 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
                     const float m = __ldg(A.mean_rstd + ch), rs = __ldg(A.mean_rstd + A.Cout + ch);
                     v.x = a4.x > 0.f ? v.x : 0.f; v.y = a4.y > 0.f ? v.y : 0.f;
                     v.z = a4.z > 0.f ? v.z : 0.f; v.w = a4.w > 0.f ? v.w : 0.f;
-                    s2 = fmaf(v.x, (x4.x - m) * rs, fmaf(v.y, (x4.y - m) * rs, fmaf(v.z, (x4.z - m) * rs, v.w * ((x4.w - m) * rs))));
-                } else {
-                    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                    s2 = static_cast<double>(v.x) * ((x4.x - m) * rs) + static_cast<double>(v.y) * ((x4.y - m) * rs) +
+                         static_cast<double>(v.z) * ((x4.z - m) * rs) + static_cast<double>(v.w) * ((x4.w - m) * rs);
+                } else if (A.stats) {
+                    s2 = static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+                         static_cast<double>(v.w) * v.w;
                 }
                 st4(A.out + off, v);
-                s1 = (v.x + v.y) + (v.z + v.w);
+                s1 = (static_cast<double>(v.x) + v.y) + (static_cast<double>(v.z) + v.w);
             }
             if (A.stats) {  // uniform branch
 #pragma unroll
@@ -230,8 +234,8 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
                     s2 += __shfl_xor_sync(0xffffffffu, s2, off);
                 }
                 if ((t & (RW - 1)) == 0 && ch < A.Cout) {
-                    atomicAdd(A.stats + ch, static_cast<double>(s1));
-                    atomicAdd(A.stats + A.Cout + ch, static_cast<double>(s2));
+                    atomicAdd(A.stats + ch, s1);
+                    atomicAdd(A.stats + A.Cout + ch, s2);
                 }
             }
         }
@@ -391,16 +395,17 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                                          float momentum, float eps, float* __restrict__ a_out,
                                                          float* __restrict__ mean_rstd, int B, int C, int HW) {
-    extern __shared__ float ks[];  // scale[C] | shift[C]
+    extern __shared__ float ks[];  // mean[C] | rstd[C] | gamma[C] | beta[C]
     const double n = static_cast<double>(B) * HW;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double m = stats[c] / n;
         double var = stats[C + c] / n - m * m;
         var = var > 0.0 ? var : 0.0;
         const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-        const float k = __ldg(gamma + c) * rstd;
-        ks[c] = k;
-        ks[C + c] = fmaf(-static_cast<float>(m), k, __ldg(beta + c));
+        ks[c] = static_cast<float>(m);
+        ks[C + c] = rstd;
+        ks[2 * C + c] = __ldg(gamma + c);
+        ks[3 * C + c] = __ldg(beta + c);
         if (blockIdx.x == 0) {
             mean_rstd[c] = static_cast<float>(m);
             mean_rstd[C + c] = rstd;
@@ -416,10 +421,12 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
     for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
          v += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(((v << 2) / HW) % C);
-        const float k = ks[c], sft = ks[C + c];
+        // subtract the mean first: x*k + (beta - mean*k) cancels when |mean| >> std; this is also exactly the xhat of
+        // the backward pass, so the ReLU mask and the gradient see the same pre-activation
+        const float m = ks[c], rs = ks[C + c], g = ks[2 * C + c], bt = ks[3 * C + c];
         const float4 q = ldg4(x + (v << 2));
-        st4(a_out + (v << 2), make_float4(fmaxf(fmaf(q.x, k, sft), 0.f), fmaxf(fmaf(q.y, k, sft), 0.f),
-                                          fmaxf(fmaf(q.z, k, sft), 0.f), fmaxf(fmaf(q.w, k, sft), 0.f)));
+        st4(a_out + (v << 2), make_float4(fmaxf(fmaf((q.x - m) * rs, g, bt), 0.f), fmaxf(fmaf((q.y - m) * rs, g, bt), 0.f),
+                                          fmaxf(fmaf((q.z - m) * rs, g, bt), 0.f), fmaxf(fmaf((q.w - m) * rs, g, bt), 0.f)));
     }
 }
 
@@ -497,6 +504,40 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
             o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
         }
         st4(gx + (v << 2), o);
+    }
+}
+
+// (B, C) rows <-> (B/HW, C, HW) channel planes: lets the 1-D (MLP) conditioner run on the convolution-layer kernels (a
+// Linear layer over rows is a 1x1 convolution over the "pixels" of a plane; BatchNorm1d statistics over the batch are
+// the BatchNorm2d statistics over (group, pixel)).  32 x 32 tiles through shared memory, both sides coalesced.
+template <bool TO_PLANES>
+__global__ void __launch_bounds__(256) rows_planes_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
+                                                         int HW) {
+    __shared__ float tile[32][33];
+    const int g = blockIdx.z;                      // group of HW rows
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const size_t rbase = static_cast<size_t>(g) * HW;        // first row of the group
+    if (TO_PLANES) {
+        for (int k = ty; k < 32; k += 8) {         // read rows (p0+k), columns c0+tx
+            const int p = p0 + k, c = c0 + tx;
+            tile[k][tx] = (p < HW && c < C) ? __ldg(src + (rbase + p) * C + c) : 0.f;
+        }
+        __syncthreads();
+        for (int k = ty; k < 32; k += 8) {         // write channel c0+k, pixels p0+tx
+            const int c = c0 + k, p = p0 + tx;
+            if (c < C && p < HW) dst[(static_cast<size_t>(g) * C + c) * HW + p] = tile[tx][k];
+        }
+    } else {
+        for (int k = ty; k < 32; k += 8) {
+            const int c = c0 + k, p = p0 + tx;
+            tile[k][tx] = (c < C && p < HW) ? __ldg(src + (static_cast<size_t>(g) * C + c) * HW + p) : 0.f;
+        }
+        __syncthreads();
+        for (int k = ty; k < 32; k += 8) {
+            const int p = p0 + k, c = c0 + tx;
+            if (p < HW && c < C) dst[(rbase + p) * C + c] = tile[tx][k];
+        }
     }
 }
 
@@ -661,7 +702,7 @@ extern "C" int nfb_bn_relu_fwd(const float* x, const double* stats, const float*
     if (B <= 0 || C <= 0 || HW <= 0) return NFB_ERR_SHAPE;
     if (HW % 4 || C > 1024 || !aligned16(x) || !aligned16(a_out)) return NFB_ERR_UNSUPPORTED;
     const long long nv = static_cast<long long>(B) * C * HW / 4;
-    bn_relu_fwd_kernel<<<ew_grid(nv), 256, sizeof(float) * 2 * C, as_stream(stream)>>>(
+    bn_relu_fwd_kernel<<<ew_grid(nv), 256, sizeof(float) * 4 * C, as_stream(stream)>>>(
         x, stats, gamma, beta, running_mean, running_var, momentum, eps, a_out, mean_rstd, B, C, HW);
     return launch_status();
 }
@@ -688,5 +729,23 @@ extern "C" int nfb_bn_bwd_apply(const float* U, const float* x, const float* mea
     const long long nv = static_cast<long long>(B) * C * HW / 4;
     bn_bwd_apply_kernel<<<ew_grid(nv), 256, sizeof(float) * 5 * C, as_stream(stream)>>>(U, x, mean_rstd, gamma, sums, add, gx,
                                                                                       g_gamma, g_beta, B, C, HW);
+    return launch_status();
+}
+
+extern "C" int nfb_rows_to_planes(const float* rows, float* planes, int B, int C, int HW, nfb_stream_t stream) {
+    if (!rows || !planes) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0 || B % HW) return NFB_ERR_SHAPE;
+    if (B / HW > 65535) return NFB_ERR_UNSUPPORTED;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B / HW);
+    rows_planes_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(rows, planes, B, C, HW);
+    return launch_status();
+}
+
+extern "C" int nfb_planes_to_rows(const float* planes, float* rows, int B, int C, int HW, nfb_stream_t stream) {
+    if (!rows || !planes) return NFB_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0 || B % HW) return NFB_ERR_SHAPE;
+    if (B / HW > 65535) return NFB_ERR_UNSUPPORTED;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B / HW);
+    rows_planes_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(planes, rows, B, C, HW);
     return launch_status();
 }

@@ -2,9 +2,9 @@
 
 ``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
 -> out_block (BN, ReLU, WN-layer).  Eval mode without autograd: ONE fused kernel over folded weights.  Train mode (batch
-statistics, modules.py:349-352): ``ConvNet`` at 16x16 / 8x8 / 4x4 runs layer by layer on libnfb200 kernels, forward and
-backward (``conditioner_train.py``); ``MLP``, other spatial sizes and eval-mode-with-gradients use cuDNN / cuBLAS ops under
-torch autograd (``_forward_autograd``).
+statistics, modules.py:349-352): ``ConvNet`` at 16x16 / 8x8 / 4x4 and ``MLP`` (batch a multiple of 16) run layer by layer
+on libnfb200 kernels, forward and backward (``conditioner_train.py``); other shapes and eval-mode-with-gradients use
+cuDNN / cuBLAS ops under torch autograd (``_forward_autograd``).
 """
 import ctypes
 
@@ -172,10 +172,20 @@ class _ResNetConditioner(nn.Module):
     native_train = True
 
     def _forward_native_train(self, x):
-        from .conditioner_train import SUPPORTED_HW, ConvNetTrainFn
-        if not (self.conv and self.training and self.native_train and x.dim() == 4 and len(self.mid_block) == 2
-                and self.base_filters == 32 and tuple(x.shape[2:]) in SUPPORTED_HW):
+        from .conditioner_train import SUPPORTED_HW, ConvNetTrainFn, RowsPlanesFn
+        if not (self.training and self.native_train and len(self.mid_block) == 2 and self.base_filters == 32):
             return None
+        hw = None
+        if self.conv:
+            if x.dim() != 4 or tuple(x.shape[2:]) not in SUPPORTED_HW:
+                return None
+        else:  # MLP: rows -> planes of hw*hw rows, then every Linear is a 1x1 convolution of the layer kernels
+            if x.dim() != 2 or x.size(0) < 16:
+                return None
+            hw = next((s for s in (16, 8, 4) if x.size(0) % (s * s) == 0 and x.size(0) // (s * s) <= 65535), None)
+            if hw is None:
+                return None
+            x = RowsPlanesFn.apply(x, hw, True)
         wn = [self.in_block[0]] + [blk.net[i] for blk in self.mid_block for i in (2, 5)] + [self.out_block[2]]
         bn = [blk.net[i] for blk in self.mid_block for i in (0, 3)] + [self.out_block[0]]
         ts = []
@@ -188,7 +198,7 @@ class _ResNetConditioner(nn.Module):
         out = ConvNetTrainFn.apply(x, (wn[0].eps, bn[0].eps, bn[0].momentum), *ts)
         for m in bn:
             m.num_batches_tracked += 1  # nn.BatchNorm bookkeeping (momentum is fixed, so it does not enter the update)
-        return out
+        return out if hw is None else RowsPlanesFn.apply(out, hw, False)
 
     def _forward_autograd(self, x):
         x = L.dev(x, 'conditioner input')

@@ -90,7 +90,37 @@ def _dgrad_bn_relu(gy, w_bwd, cin, ks, a, x, mr, gamma, add, sums):
     return gx, gg, gb
 
 
+class RowsPlanesFn(Function):
+    """(B, C) rows -> (B/HW, C, h, w) planes (to_planes) or back; the gradient is the opposite transposition."""
+
+    @staticmethod
+    def forward(ctx, x, hw, to_planes):
+        x = L.dev(x, 'conditioner tensor')
+        ctx.meta = (hw, to_planes)
+        return _rows_planes(x, hw, to_planes)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        hw, to_planes = ctx.meta
+        return _rows_planes(L.dev(g, 'grad'), hw, not to_planes), None, None
+
+
+def _rows_planes(x, hw, to_planes):
+    if to_planes:
+        B, C = x.shape
+        out = torch.empty((B // (hw * hw), C, hw, hw), device=x.device, dtype=torch.float32)
+        L.check(L.lib().nfb_rows_to_planes(L.ptr(x), L.ptr(out), B, C, hw * hw, L.stream()))
+    else:
+        G, C = x.shape[:2]
+        B = G * hw * hw
+        out = torch.empty((B, C), device=x.device, dtype=torch.float32)
+        L.check(L.lib().nfb_planes_to_rows(L.ptr(x), L.ptr(out), B, C, hw * hw, L.stream()))
+    return out
+
+
 class ConvNetTrainFn(Function):
+    """Also serves the MLP conditioner: with 2-D weights every layer is a 1x1 convolution over planes of rows."""
 
     @staticmethod
     def forward(ctx, x, cfg, *T):
@@ -98,6 +128,7 @@ class ConvNetTrainFn(Function):
         wn, bn, rs = T[:18], T[18:28], T[28:38]
         wn_eps, bn_eps, momentum = cfg
         cin, cout = wn[0].size(1), wn[15].size(0)
+        k3 = 3 if wn[0].dim() == 4 and wn[0].size(2) == 3 else 1  # ConvNet: 3x3 body; MLP (2-D weights): all 1x1
         packed, ptrs, dims, keep = [], [], [], []
         for i in range(6):  # WeightNorm + packing of all six layers: one launch
             v, g = wn[3 * i], wn[3 * i + 1]
@@ -120,21 +151,21 @@ class ConvNetTrainFn(Function):
 
         arena = torch.zeros(5 * 2 * F32, device=x.device, dtype=torch.float64)  # the five moment accumulators, one fill
         acc = [arena[i * 2 * F32:(i + 1) * 2 * F32] for i in range(5)]
-        h0, st = _conv(x, packed[0][0], b[0], None, cin, F32, 3, True, acc[0])
+        h0, st = _conv(x, packed[0][0], b[0], None, cin, F32, k3, True, acc[0])
         a1, mr1 = bnr(h0, st, 0)
-        y1, st = _conv(a1, packed[1][0], b[1], None, F32, F32, 3, True, acc[1])
+        y1, st = _conv(a1, packed[1][0], b[1], None, F32, F32, k3, True, acc[1])
         a2, mr2 = bnr(y1, st, 1)
-        h1, st = _conv(a2, packed[2][0], b[2], h0, F32, F32, 3, True, acc[2])
+        h1, st = _conv(a2, packed[2][0], b[2], h0, F32, F32, k3, True, acc[2])
         a3, mr3 = bnr(h1, st, 2)
-        y2, st = _conv(a3, packed[3][0], b[3], None, F32, F32, 3, True, acc[3])
+        y2, st = _conv(a3, packed[3][0], b[3], None, F32, F32, k3, True, acc[3])
         a4, mr4 = bnr(y2, st, 3)
-        h2, st = _conv(a4, packed[4][0], b[4], h1, F32, F32, 3, True, acc[4])
+        h2, st = _conv(a4, packed[4][0], b[4], h1, F32, F32, k3, True, acc[4])
         a5, mr5 = bnr(h2, st, 4)
         out, _ = _conv(a5, packed[5][0], b[5], None, F32, cout, 1, False)
         ctx.save_for_backward(x, h0, a1, y1, a2, h1, a3, y2, a4, h2, a5, mr1, mr2, mr3, mr4, mr5,
                               *[p[1] for p in packed], *[wn[3 * i] for i in range(6)], *[wn[3 * i + 1] for i in range(6)],
                               *gam)
-        ctx.meta = (cin, cout, float(wn_eps))
+        ctx.meta = (cin, cout, float(wn_eps), k3)
         return out
 
     @staticmethod
@@ -143,7 +174,7 @@ class ConvNetTrainFn(Function):
         S = ctx.saved_tensors
         x, h0, a1, y1, a2, h1, a3, y2, a4, h2, a5, mr1, mr2, mr3, mr4, mr5 = S[:16]
         wb, vs, gs, gam = S[16:22], S[22:28], S[28:34], S[34:39]
-        cin, cout, wn_eps = ctx.meta
+        cin, cout, wn_eps, k3 = ctx.meta
         gout = L.dev(gout, 'grad params')
         gw, gb, ggam, gbet = [None] * 6, [None] * 6, [None] * 5, [None] * 5
         # out block
@@ -154,14 +185,14 @@ class ConvNetTrainFn(Function):
         # residual blocks, last first: (layer indices, BatchNorm indices, activations)
         for (l2, l1, bB, bA, aB, yB, mrB, aA, hA, mrA) in ((4, 3, 3, 2, a4, y2, mr4, a3, h1, mr3),
                                                           (2, 1, 1, 0, a2, y1, mr2, a1, h0, mr1)):
-            gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, 3)
-            gy, ggam[bB], gbet[bB] = _dgrad_bn_relu(G, wb[l2], F32, 3, aB, yB, mrB, gam[bB], None, acc[bB])
-            gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, 3)
-            G, ggam[bA], gbet[bA] = _dgrad_bn_relu(gy, wb[l1], F32, 3, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
-        gw[0], gb[0] = _wgrad(G, x, cin, F32, 3)
+            gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, k3)
+            gy, ggam[bB], gbet[bB] = _dgrad_bn_relu(G, wb[l2], F32, k3, aB, yB, mrB, gam[bB], None, acc[bB])
+            gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, k3)
+            G, ggam[bA], gbet[bA] = _dgrad_bn_relu(gy, wb[l1], F32, k3, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
+        gw[0], gb[0] = _wgrad(G, x, cin, F32, k3)
         gx = None
         if ctx.needs_input_grad[0]:
-            gx, _ = _conv(G, wb[0], None, None, F32, cin, 3, False)
+            gx, _ = _conv(G, wb[0], None, None, F32, cin, k3, False)
         grads, ptrs, dims = [], [], []
         for i in range(6):  # WeightNorm backward of all six layers: one launch
             v, g = vs[i], gs[i]

@@ -82,3 +82,17 @@ def grad_close(got, want, rtol, what='', floor=2e-6):
     err = float((got - want).abs().max())
     assert err <= rtol * max(scale, 1e-12) + 1e-30 or err <= max(floor, 2e-6), '%s: max err %.3e vs scale %.3e (rtol %.1e)' % (
         what, err, scale, rtol)
+
+
+def grad_close_yardstick(got, ref32, truth64, rtol, what='', floor=2e-6, slack=4.0):
+    """Deep / ill-conditioned stacks amplify fp32 rounding in ANY implementation (e.g. a weight in front of a train-mode
+    BatchNorm is scale-invariant: its gradient is the small residue of large cancelling terms), so the yardstick is the
+    fp64 run of the oracle: `got` may be at most `slack` times as far from the fp64 truth as the reference's own fp32
+    result `ref32` is, plus the usual relative tolerance."""
+    got, ref32, truth64 = [t.detach().cpu().double().reshape(-1) for t in (got, ref32, truth64)]
+    assert got.shape == truth64.shape, (what, got.shape, truth64.shape)
+    scale = float(truth64.abs().max())
+    e_got = float((got - truth64).abs().max())
+    e_ref = float((ref32 - truth64).abs().max())
+    assert e_got <= slack * e_ref + rtol * max(scale, 1e-12) + max(floor, 2e-6), \
+        '%s: |gpu - fp64| %.3e, |fp32 reference - fp64| %.3e, scale %.3e (rtol %.1e)' % (what, e_got, e_ref, scale, rtol)

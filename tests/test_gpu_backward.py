@@ -94,8 +94,9 @@ def test_model_gradients_vs_reference_golden(name):
     want = {k[5:]: v for k, v in a.items() if k.startswith('grad/')}
     assert set(want) <= set(got), sorted(set(want) - set(got))
     floor = GC.grad_floor(want)
+    _, g64 = GC.oracle_model_grads(meta, sd, src['x'], torch.float64)  # fp64 truth: the yardstick for deep stacks
     for k, v in want.items():
-        GC.grad_close(got[k], v, 5e-4, k, floor)
+        GC.grad_close_yardstick(got[k], v, g64[k], 5e-4, k, floor)
     for k, v in a.items():
         if k.startswith('after/'):
             GC.grad_close(net.state_dict()[k[6:]], v, 5e-5, k)
@@ -302,6 +303,7 @@ def test_training_step_gradients_vs_oracle(cfg):
     loss = rows.mean()
     loss.backward()
     lo, go = GC.oracle_model_grads(meta, sd, x, torch.float32, True, cfg.get('coupling'))
+    _, g64 = GC.oracle_model_grads(meta, sd, x, torch.float64, True, cfg.get('coupling'))
     assert abs(float(loss) - float(lo)) <= 2e-5 * abs(float(lo))
     got = named_grads(net)
     buffers = dict(net.named_buffers())
@@ -309,7 +311,7 @@ def test_training_step_gradients_vs_oracle(cfg):
     for k, v in go.items():
         if k in buffers:  # e.g. log_gamma / beta of BatchNorm(affine=False): buffers, not trained (modules.py:269-273)
             continue
-        GC.grad_close(got[k], v, 1e-3, k, floor)
+        GC.grad_close_yardstick(got[k], v, g64[k], 1e-3, k, floor)
 
 
 def test_training_reduces_loss_and_matches_eval_path():
@@ -463,3 +465,43 @@ def test_bn_relu_kernels_vs_torch(hw, B):
     GC.grad_close(gx, xd.grad + add.double(), 1e-5, 'gx')
     GC.grad_close(gg, gd.grad, 1e-5, 'g gamma')
     GC.grad_close(gb, bd.grad, 1e-5, 'g beta')
+
+
+@pytest.mark.parametrize('cin,cout,B', [(32, 736, 512), (1, 2, 512), (3, 6, 64), (32, 64, 4096), (5, 10, 48)])
+def test_native_train_mlp_vs_library(cin, cout, B):
+    """Train-mode MLP conditioner (1-D couplings) on the layer kernels -- rows transposed into planes, every Linear a 1x1
+    convolution -- against cuBLAS / ATen under torch autograd."""
+    F = nfb().flows
+    torch.manual_seed(4)
+    net = F.MLP(cin, cout)
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith('.weight') and p.dim() == 1:
+                p.add_(0.2 * torch.randn(p.shape, generator=gen))
+            elif name.endswith('.bias'):
+                p.add_(0.1 * torch.randn(p.shape, generator=gen))
+    net.to(DEV).train()
+    snap = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(B, cin, generator=gen).to(DEV)
+    R = torch.randn(B, cout, generator=gen).to(DEV)
+    res = []
+    for native in (True, False):
+        net.native_train = native
+        net.load_state_dict(snap)
+        net.zero_grad(set_to_none=True)
+        xx = x.clone().requires_grad_(True)
+        n0 = nfb()._lib.launch_count()
+        out = net(xx)
+        (out * R).sum().backward()
+        assert ((nfb()._lib.launch_count() - n0) >= 20) == native
+        res.append((out.detach(), xx.grad, {k: p.grad.clone() for k, p in net.named_parameters()},
+                    {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k}))
+    (o1, g1, p1, s1), (o0, g0, p0, s0) = res
+    GC.grad_close(o1, o0, 2e-5, 'out')
+    floor = GC.grad_floor(p0)
+    GC.grad_close(g1, g0, 2e-4, 'gx', floor)
+    for k in p0:
+        GC.grad_close(p1[k], p0[k], 2e-4, k, floor)
+    for k in s0:
+        GC.grad_close(s1[k].float(), s0[k].float(), 2e-5, k)
