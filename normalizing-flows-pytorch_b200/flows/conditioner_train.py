@@ -45,7 +45,10 @@ def _bn_relu(x, stats, gamma, beta, rmean, rvar, momentum, eps):
     return a, mr
 
 
-def _wgrad(gy, a, cin, cout, ks):
+def _wgrad(gy, a, cin, cout, ks, side=None, keep=None):
+    """Weight / bias gradient.  With `side` (a CUDA stream) the kernels are enqueued there, after everything issued so far
+    on the current stream, so they overlap with the data-gradient chain that follows; the caller joins the streams before
+    it reads the results and holds `keep` (the scratch buffers) until then."""
     B, _, h, w = gy.shape
     gw = torch.empty((cout, cin, ks, ks), device=gy.device, dtype=torch.float32)
     gb = torch.empty(cout, device=gy.device, dtype=torch.float32)
@@ -53,9 +56,25 @@ def _wgrad(gy, a, cin, cout, ks):
     if n < 0:
         L.check(n)
     scratch = torch.empty(n, device=gy.device, dtype=torch.float32)  # per-sample-group partial sums (no zero-fill needed)
-    L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), L.ptr(scratch), B, cin, cout, h, w, ks,
-                                         L.stream()))
+    if side is None:
+        L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), L.ptr(scratch), B, cin, cout, h, w,
+                                             ks, L.stream()))
+    else:
+        keep.extend([scratch, gy, a])  # allocated on the main stream: must outlive the side-stream kernels that use them
+        side.wait_stream(torch.cuda.current_stream())
+        L.check(L.lib().nfb_conv_train_wgrad(L.ptr(gy), L.ptr(a), L.ptr(gw), L.ptr(gb), L.ptr(scratch), B, cin, cout, h, w,
+                                             ks, side.cuda_stream))
     return gw, gb
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def _bn_relu_bwd(ga, a, x, mr, gamma, add, sums=None):
@@ -122,6 +141,10 @@ def _rows_planes(x, hw, to_planes):
 class ConvNetTrainFn(Function):
     """Also serves the MLP conditioner: with 2-D weights every layer is a 1x1 convolution over planes of rows."""
 
+    # weight gradients on a second stream: they only feed the WeightNorm backward at the very end, so they run next to the
+    # data-gradient / BatchNorm-backward chain and fill the SMs its 256-CTA launches leave idle (also inside graph capture)
+    overlap_wgrad = True
+
     @staticmethod
     def forward(ctx, x, cfg, *T):
         x = L.dev(x, 'conditioner input')
@@ -177,22 +200,26 @@ class ConvNetTrainFn(Function):
         cin, cout, wn_eps, k3 = ctx.meta
         gout = L.dev(gout, 'grad params')
         gw, gb, ggam, gbet = [None] * 6, [None] * 6, [None] * 5, [None] * 5
+        side = _side_stream(gout.device) if ConvNetTrainFn.overlap_wgrad else None
+        keep = []
         # out block
-        gw[5], gb[5] = _wgrad(gout, a5, F32, cout, 1)
+        gw[5], gb[5] = _wgrad(gout, a5, F32, cout, 1, side, keep)
         arena = torch.zeros(5 * 2 * F32, device=gout.device, dtype=torch.float64)  # the five BatchNorm-backward sum pairs
         acc = [arena[i * 2 * F32:(i + 1) * 2 * F32] for i in range(5)]
         G, ggam[4], gbet[4] = _dgrad_bn_relu(gout, wb[5], cout, 1, a5, h2, mr5, gam[4], None, acc[4])
         # residual blocks, last first: (layer indices, BatchNorm indices, activations)
         for (l2, l1, bB, bA, aB, yB, mrB, aA, hA, mrA) in ((4, 3, 3, 2, a4, y2, mr4, a3, h1, mr3),
                                                           (2, 1, 1, 0, a2, y1, mr2, a1, h0, mr1)):
-            gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, k3)
+            gw[l2], gb[l2] = _wgrad(G, aB, F32, F32, k3, side, keep)
             gy, ggam[bB], gbet[bB] = _dgrad_bn_relu(G, wb[l2], F32, k3, aB, yB, mrB, gam[bB], None, acc[bB])
-            gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, k3)
+            gw[l1], gb[l1] = _wgrad(gy, aA, F32, F32, k3, side, keep)
             G, ggam[bA], gbet[bA] = _dgrad_bn_relu(gy, wb[l1], F32, k3, aA, hA, mrA, gam[bA], G, acc[bA])  # + the skip branch
-        gw[0], gb[0] = _wgrad(G, x, cin, F32, k3)
+        gw[0], gb[0] = _wgrad(G, x, cin, F32, k3, side, keep)
         gx = None
         if ctx.needs_input_grad[0]:
             gx, _ = _conv(G, wb[0], None, None, F32, cin, k3, False)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)  # every weight gradient has landed
         grads, ptrs, dims = [], [], []
         for i in range(6):  # WeightNorm backward of all six layers: one launch
             v, g = vs[i], gs[i]

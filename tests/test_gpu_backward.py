@@ -505,3 +505,30 @@ def test_native_train_mlp_vs_library(cin, cout, B):
         GC.grad_close(p1[k], p0[k], 2e-4, k, floor)
     for k in s0:
         GC.grad_close(s1[k].float(), s0[k].float(), 2e-5, k)
+
+
+def test_side_stream_weight_gradients_are_identical():
+    """The weight-gradient kernels run on a second stream next to the data-gradient chain (ConvNetTrainFn.overlap_wgrad);
+    they are deterministic (no atomics), so both schedules must give bit-identical gradients -- eager and captured."""
+    nfb()
+    from nfb200.flows import conditioner_train as CT
+    F = nfb().flows
+    torch.manual_seed(7)
+    net = F.ConvNet(24, 48).to(DEV).train()
+    snap = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(64, 24, 8, 8, device=DEV)
+    R = torch.randn(64, 48, 8, 8, device=DEV)
+    res = []
+    try:
+        for overlap in (True, False, True):
+            CT.ConvNetTrainFn.overlap_wgrad = overlap
+            net.load_state_dict(snap)
+            net.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_(True)
+            (net(xx) * R).sum().backward()
+            torch.cuda.synchronize()
+            res.append([xx.grad.clone()] + [p.grad.clone() for p in net.parameters()])
+    finally:
+        CT.ConvNetTrainFn.overlap_wgrad = True
+    for a, b, c in zip(*res):
+        assert torch.equal(a, b) and torch.equal(a, c)
