@@ -219,6 +219,14 @@ int nfb_pack_conv3x3(const float* w, float* out, int O, int I, nfb_stream_t stre
 int nfb_flowpp_cond_fwd(const float* const* tensors, const float* src, float* params_out, int B, int C, int H, int W,
                         int mode, int odd, int in_ch, int out_ch, nfb_stream_t stream);
 
+/* Flow++ conditioner of the 1-D couplings (coupling.py:142-158: Linear -> GatedLinear -> LayerNorm -> GatedAttn -> LayerNorm
+ * -> Linear; a 1-D input is a single attention token, so A = Q exactly) as ONE kernel.  `tensors`: HOST array of the same
+ * 15 device pointers as nfb_flowpp_cond_fwd, all UNPACKED (net.0.weight (32,in), net.1.op.weight (32,64), net.5.weight
+ * (out,32)).  mode = NFB_SPLIT_1D: src = z (B, D), z1 gathered; mode < 0: src = (B, in_ch).  NFB_ERR_UNSUPPORTED when the
+ * network does not fit in shared memory. */
+int nfb_flowpp_mlp_fwd(const float* const* tensors, const float* src, float* params_out, int B, int D, int mode, int odd,
+                       int in_ch, int out_ch, nfb_stream_t stream);
+
 /* params_out (B, out_ch) = MLP(z1).  mode = NFB_SPLIT_1D: src = z (B, C), z1 gathered (squeeze.py:64-72);
  * mode < 0: src = (B, in_ch). */
 int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd, int in_ch,

@@ -56,6 +56,7 @@ _SIGNATURES = {
     'nfb_glow_step_fwd': [_P] * 11 + [_I] * 6 + [_P],
     'nfb_pack_conv3x3': [_P, _P, _I, _I, _P],
     'nfb_flowpp_cond_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_flowpp_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nfb_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nfb_affine_coupling_bwd': [_P] * 11 + [_I] * 6 + [_P],
     'nfb_mixlog_coupling_bwd': [_P] * 11 + [_I] * 7 + [_P],

@@ -164,8 +164,18 @@ class MixLogAttnCoupling(AbstractCoupling):
             self._fpp_key = key
         return self._fpp_arr
 
+    def _fpp_tensors_1d(self):
+        """Host array of the 15 raw parameter pointers (nothing is packed for the 1-D kernel); rebuilt after .to()."""
+        if getattr(self, '_fpp_arr1d', None) is None:
+            n = self.net
+            ts = [n[0].weight, n[0].bias, n[1].op.weight, n[1].op.bias, n[2].weight, n[2].bias, n[3].pos_emb,
+                  n[3].conv1.weight, n[3].conv1.bias, n[3].conv2.weight, n[3].conv2.bias, n[4].weight, n[4].bias,
+                  n[5].weight, n[5].bias]
+            self._fpp_arr1d = (ctypes.c_void_p * 15)(*[L.ptr(L.dev(t.data, 'conditioner parameter')) for t in ts])
+        return self._fpp_arr1d
+
     def _apply(self, fn, *a, **k):
-        self._fpp_ts = self._fpp_key = None
+        self._fpp_ts = self._fpp_key = self._fpp_arr1d = None
         return super()._apply(fn, *a, **k)
 
     def _params(self, z):
@@ -180,7 +190,17 @@ class MixLogAttnCoupling(AbstractCoupling):
             if rc != L.ERR_UNSUPPORTED:
                 L.check(rc)
                 return out
-        # library path (torch ops on the device): 1-D inputs, spatial sizes the kernel does not cover, train mode
+        if z.dim() == 2 and not self.net.training and self.fused_conditioner and not self._recording(z, z):
+            # 1-D couplings: the whole conditioner is one per-sample kernel (a single attention token: A = Q)
+            ts = self._fpp_tensors_1d()
+            n_out = sum(self.sections)
+            out = torch.empty((z.size(0), n_out), device=z.device, dtype=torch.float32)
+            rc = L.lib().nfb_flowpp_mlp_fwd(ts, L.ptr(z), L.ptr(out), z.size(0), z.size(1), self.mode, int(self.odd),
+                                            z.size(1) // 2, n_out, L.stream())
+            if rc != L.ERR_UNSUPPORTED:
+                L.check(rc)
+                return out
+        # library path (torch ops on the device): spatial sizes the kernels do not cover, train mode
         z1 = self._z1(z)
         return L.dev(self.net(z1), 'conditioner output')
 

@@ -612,6 +612,56 @@ def test_flowpp_conditioner_kernel_vs_oracle(dims, masking, K, B):
     assert e_f <= 6.0 * max(e_r, e_l) + 1e-6 * scale
 
 
+@pytest.mark.parametrize('D,K,B', [(2, 4, 512), (6, 8, 257), (64, 8, 1000), (2, 1, 5)])
+@pytest.mark.parametrize('odd', [False, True])
+def test_flowpp_conditioner_1d_kernel_vs_oracle(D, K, B, odd):
+    """One-kernel Flow++ conditioner of the 1-D couplings (single attention token: A = Q) vs the CPU oracle, and the whole
+    1-D Flow++ stack (flowpp.py:64-66: ActNorm + coupling per step) forward / inverse vs the oracle."""
+    n = nfb()
+    torch.manual_seed(K + D)
+    cpl = n.flows.MixLogAttnCoupling((D, ), odd=odd, n_mixtures=K)
+    with torch.no_grad():
+        for n_, p in cpl.named_parameters():
+            if 'pos_emb' in n_:
+                p.add_(0.1 * torch.randn(p.shape))
+            elif n_.endswith(('2.weight', '4.weight')):
+                p.add_(0.2 * torch.randn(p.shape))
+            elif n_.endswith(('2.bias', '4.bias')):
+                p.add_(0.1 * torch.randn(p.shape))
+    cpl.eval()
+    sd = {k: v.clone() for k, v in cpl.state_dict().items()}
+    z = torch.randn(B, D)
+    split, _ = O.split_fn(1, 'checkerboard', odd)
+    with torch.no_grad():
+        ref = O.flowpp_conditioner(sd, 'net.', split(z)[1])
+        ref64 = O.flowpp_conditioner(O.to_dtype(sd, torch.float64), 'net.', split(z)[1].double())
+    cpl.to(DEV)
+    n0 = n._lib.launch_count()
+    fused = cpl._params(z.to(DEV))
+    assert n._lib.launch_count() - n0 == 1  # one libnfb200 kernel, no library ops
+    scale = max(1.0, float(ref.abs().max()))
+    e_f = float((fused.cpu().double() - ref64).abs().max())
+    e_r = float((ref.double() - ref64).abs().max())
+    close(fused, ref, rtol=2e-5, atol=5e-6 * scale, what='fused 1-D flow++ conditioner vs oracle')
+    assert e_f <= 6.0 * e_r + 1e-6 * scale
+    if D == 2:  # the 2-D toy densities of the reference (dataset.py:18-60): whole stack
+        torch.manual_seed(1)
+        net = n.Flowpp((2, ), None, types.SimpleNamespace(layers=4, mixtures=K))
+        perturb_(net)
+        net.mark_initialized().eval()
+        msd = {k: v.clone() for k, v in net.state_dict().items()}
+        x = torch.rand(B, 2) * 2 - 1
+        spec = oracle_spec('flowpp', (2, ), None, 4, K)
+        with torch.no_grad():
+            zo, lo = O.stack_forward(spec, msd, x)
+        net.to(DEV)
+        zg, lg = net(x.to(DEV))
+        close(zg, zo, rtol=2e-5, atol=2e-5, what='1-D flow++ stack z')
+        close(lg, lo, rtol=2e-5, atol=2e-4, what='1-D flow++ stack ldj')
+        y, _ = net.backward(zg)
+        close(y, x, rtol=1e-3, atol=1e-3, what='1-D flow++ round trip')
+
+
 def test_sharded_statistics_match_global_batch():
     """ActNorm init / BatchNorm train statistics from per-shard moments (what the ranks all-reduce) == full-batch pass."""
     n = nfb()
