@@ -87,7 +87,8 @@ class _ResNetConditioner(nn.Module):
         return self._pack
 
     def _fused_ok(self, x):
-        """The fused kernel is the eval-mode inference path; train mode and autograd go through torch ops."""
+        """The fused kernel is the eval-mode inference path; train mode and autograd take `_forward_autograd` (libnfb200
+        layer kernels where they apply, torch ops otherwise)."""
         if self.training:
             return False
         return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
@@ -132,7 +133,7 @@ class _ResNetConditioner(nn.Module):
         L.check(rc)
         return out
 
-    # -- library path (cuDNN / cuBLAS through torch, TF32 off): only for conditioner inputs whose spatial size the
+    # -- library path (cuDNN / cuBLAS through torch, TF32 off): only for eval-mode conditioner inputs whose spatial size the
     #    fused kernel does not cover yet (anything but 16x16 / 8x8 / 4x4, e.g. the 32x32 level of a 64x64 Glow), and
     #    as an on-device cross-check in the tests -------------------------------------------------------------
     def _layer(self, wn, x):
@@ -168,7 +169,7 @@ class _ResNetConditioner(nn.Module):
             return F.conv2d(x, w, wn.module.bias, 1, (w.size(2) - 1) // 2)
         return F.linear(x, w, wn.module.bias)
 
-    # train mode on libnfb200 kernels (ConvNet at 16x16 / 8x8 / 4x4); False = cuDNN / cuBLAS ops under torch autograd
+    # train mode on libnfb200 kernels (ConvNet at 16x16 / 8x8 / 4x4, MLP); False = cuDNN / cuBLAS ops under torch autograd
     native_train = True
 
     def _forward_native_train(self, x):
@@ -226,7 +227,9 @@ class ConvNet(_ResNetConditioner):
     conv = True
 
 
-# ---- Flow++ conditioner pieces (modules.py:500-578) -- torch ops on the device for now ----
+# ---- Flow++ conditioner pieces (modules.py:500-578): parameter holders with the reference's keys.  Inference runs them as
+#      one kernel (nfb_flowpp_cond_fwd / nfb_flowpp_mlp_fwd, see coupling.py); these torch-op forwards serve train mode,
+#      autograd and the spatial sizes the kernels do not cover ----
 
 
 class GatedLinear(nn.Module):

@@ -136,8 +136,8 @@ def train_step(model, optimizer, x_local, group=None):
 
 class GraphedTrainStep:
     """The training step as CUDA-graph replays: graph 1 = train-mode forward + loss + backward (every libnfb200 kernel,
-    the conditioner's cuDNN / cuBLAS calls and torch's glue captured once), then the gradient all-reduce on the flat
-    bucket, then a fused multi-tensor optimizer step (``capturable`` Adam inside graph 2).  The eager step of a Glow K=32
+    any library call of a conditioner that is not covered natively, and torch's glue captured once), then the gradient
+    all-reduce on the flat bucket, then a fused multi-tensor optimizer step (``capturable`` Adam inside graph 2).  The eager step of a Glow K=32
     is dominated by Python / launch overhead (thousands of small launches); replaying removes it.
 
     All parameter gradients are views into ONE flat fp32 buffer, so the all-reduce needs no gather / scatter copies and
