@@ -286,7 +286,7 @@ int nfb_gauss_nll_bwd(const float* z, const float* g_rows, float* gz, float* gld
 
 /* ---------------- train-mode ConvNet conditioner (modules.py:416-438 under net.train()) and its backward ----------------
  * BatchNorm on batch statistics makes every layer depend on the whole batch, so the network runs layer by layer over
- * (B, 32, h, w) activations (h x w in {16x16, 8x8, 4x4}; else NFB_ERR_UNSUPPORTED and the caller uses the library path).
+ * (B, 32, h, w) activations (h x w in {32x32, 16x16, 8x8, 4x4}; else NFB_ERR_UNSUPPORTED and the caller uses the library path).
  * nfb200/flows/conditioner_train.py strings these together as one autograd function. */
 
 /* WeightNorm (weight_norm.py:40) of v (O, I, KK) / g (I, KK), KK in {1, 9}: w_nat (O, I, KK) plus the two packed layouts

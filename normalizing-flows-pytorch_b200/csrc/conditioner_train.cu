@@ -135,11 +135,15 @@ struct ConvArgs {
     const float* mean_rstd;
 };
 
-template <int H, int W, int NT, int OCT, int KS>
+// TILES > 1: the image is H * TILES rows high and a CTA owns one horizontal band of H rows of one sample (32x32 inputs
+// as four 8 x 32 bands); its halo rows come from the neighbouring bands in global memory instead of being zero.
+template <int H, int W, int NT, int OCT, int KS, int TILES>
 __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
     constexpr int KK = KS * KS;
+    constexpr int HF = H * TILES;  // full image height
     constexpr int PGS = H * W / 4, NOG = kF / OCT, NPG = NT / NOG, S = NPG / PGS;
     static_assert(S >= 1 && S * PGS == NPG, "tile must hold whole samples");
+    static_assert(TILES == 1 || S == 1, "banded images: one band per CTA");
     constexpr int CHS = S * (H + 2) * W;
     constexpr int RW = NPG < 32 ? NPG : 32;  // lanes that share one output-channel group inside a warp
     extern __shared__ __align__(16) float smem[];
@@ -149,7 +153,8 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
     const int pg = t % NPG, og = t / NPG;
     const int s = pg / PGS, r = pg % PGS;
     const int y = r / (W / 4), x0 = 4 * (r % (W / 4));
-    const int b = blockIdx.x * S + s;
+    const int b = TILES == 1 ? blockIdx.x * S + s : blockIdx.x / TILES;
+    const int r0 = TILES == 1 ? 0 : (blockIdx.x % TILES) * H;  // first image row of this CTA's band
     const bool valid = b < A.B;
     const int sbase = s * (H + 2) * W;
     const int n_ic = (A.Cin + 31) >> 5, n_oc = (A.Cout + 31) >> 5;
@@ -162,7 +167,20 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
         for (int o = 0; o < OCT; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
         for (int ic = 0; ic < n_ic; ++ic) {
             __syncthreads();  // previous chunk fully consumed (also orders the zero fill)
-            if (n_ic > 1 || oc == 0) {
+            if (TILES > 1 && (n_ic > 1 || oc == 0)) {
+                // band + its two halo rows: image rows r0-1 .. r0+H (zeros outside the image)
+                constexpr int RWv = W / 4;
+                for (int i = t; i < kF * (H + 2) * RWv; i += NT) {
+                    const int ci = i / ((H + 2) * RWv);
+                    const int rem = i - ci * ((H + 2) * RWv);
+                    const int rr = rem / RWv, xv = rem - rr * RWv;
+                    const int gr = r0 + rr - 1, ch = ic * 32 + ci;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && ch < A.Cin && gr >= 0 && gr < HF)
+                        v = ldg4(A.in + ((static_cast<size_t>(b) * A.Cin + ch) * HF + gr) * W + 4 * xv);
+                    st4(bufA + ci * CHS + rr * W + 4 * xv, v);
+                }
+            } else if (n_ic > 1 || oc == 0) {
                 // input chunk: channels [32 ic, 32 ic + 32) of the CTA's S samples, float4 per thread
                 for (int i = t; i < kF * S * HWv; i += NT) {
                     const int ci = i / (S * HWv);
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
             if (valid && ch < A.Cout) {
                 const float bias = A.bias ? __ldg(A.bias + ch) : 0.f;
                 float4 v = make_float4(acc[o][0] + bias, acc[o][1] + bias, acc[o][2] + bias, acc[o][3] + bias);
-                const size_t off = ((static_cast<size_t>(b) * A.Cout + ch) * H + y) * W + x0;
+                const size_t off = ((static_cast<size_t>(b) * A.Cout + ch) * HF + r0 + y) * W + x0;
                 if (A.skip) {
                     const float4 k = ldg4(A.skip + off);
                     v.x += k.x; v.y += k.y; v.z += k.z; v.w += k.w;
@@ -242,17 +260,17 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
     }
 }
 
-template <int H, int W, int NT, int OCT, int KS>
+template <int H, int W, int NT, int OCT, int KS, int TILES = 1>
 static int launch_conv_layer(const ConvArgs& A, cudaStream_t st) {
     constexpr int S = (NT / (kF / OCT)) / (H * W / 4);
     constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 32 * KS * KS * 32) * sizeof(float);
-    auto kern = conv_layer_kernel<H, W, NT, OCT, KS>;
+    auto kern = conv_layer_kernel<H, W, NT, OCT, KS, TILES>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         attr_set = true;
     }
-    kern<<<(A.B + S - 1) / S, NT, smem, st>>>(A);
+    kern<<<TILES == 1 ? (A.B + S - 1) / S : A.B * TILES, NT, smem, st>>>(A);
     return launch_status();
 }
 
@@ -273,10 +291,14 @@ __device__ __forceinline__ void load_row(float (&dst)[W], const float* __restric
 
 // SPI samples are staged per iteration (16 image rows in every configuration: 1 x 16, 4 x 8 or 8 x 4), so the small
 // feature maps do not pay two block barriers per 16 pixels.
-template <int H, int W, int KS, int SPI>
+// TILES > 1 (SPI = 1): a work unit is one horizontal band of H rows of one sample (image height H * TILES); the halo rows
+// of `a` come from the neighbouring bands.  B then counts units (samples x TILES).
+template <int H, int W, int KS, int SPI, int TILES>
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ a,
                                                    float* __restrict__ partial, int Cin, int Cout, int B, int spc) {
     constexpr int KK = KS * KS;
+    constexpr int HF = H * TILES;
+    static_assert(TILES == 1 || SPI == 1, "banded images: one band per iteration");
     constexpr int GS = SPI * H * W + 4;          // channel stride of the gy tile (stride/4 odd: conflict-free float4 reads)
     constexpr int AS = SPI * (H + 2) * W + 4;    // channel stride of the a tile (zero rows above / below every sample)
     static_assert(((GS / 4) & 1) == 1 && ((AS / 4) & 1) == 1, "padded strides");
@@ -301,6 +323,25 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ gy
     const int b1 = (b0 + spc) < B ? (b0 + spc) : B;
     for (int b = b0; b < b1; b += SPI) {
         __syncthreads();
+        if (TILES > 1) {
+            const int smp = b / TILES, r0 = (b % TILES) * H;
+            constexpr int RWv = W / 4;
+            for (int i = t; i < 32 * (H + 2) * RWv; i += 256) {
+                const int ch = i / ((H + 2) * RWv);
+                const int rem = i - ch * ((H + 2) * RWv);
+                const int rr = rem / RWv, xv = rem - rr * RWv;
+                const int gr = r0 + rr - 1;  // image row of padded row rr
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ic * 32 + ch < Cin && gr >= 0 && gr < HF)
+                    a4 = ldg4(a + ((static_cast<size_t>(smp) * Cin + ic * 32 + ch) * HF + gr) * W + 4 * xv);
+                st4(as + ch * AS + rr * W + 4 * xv, a4);
+                if (rr >= 1 && rr <= H) {
+                    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (oc * 32 + ch < Cout) g4 = ldg4(gy + ((static_cast<size_t>(smp) * Cout + oc * 32 + ch) * HF + gr) * W + 4 * xv);
+                    st4(gys + ch * GS + (rr - 1) * W + 4 * xv, g4);
+                }
+            }
+        } else
         for (int i = t; i < 32 * SPI * HWv; i += 256) {
             const int ch = i / (SPI * HWv);
             int rem = i - ch * (SPI * HWv);
@@ -617,6 +658,8 @@ static int conv_dispatch(const ConvArgs& A, int h, int w, int ks, cudaStream_t s
     if (h == 8 && w == 8) { NFB_CL(8, 8, 128, 4); }
     if (h == 4 && w == 4) { NFB_CL(4, 4, 128, 2); }
 #undef NFB_CL
+    if (h == 32 && w == 32)  // four 8 x 32 bands per sample
+        return ks == 3 ? launch_conv_layer<8, 32, 256, 8, 3, 4>(A, st) : launch_conv_layer<8, 32, 256, 8, 1, 4>(A, st);
     return NFB_ERR_UNSUPPORTED;
 }
 
@@ -645,8 +688,12 @@ extern "C" int nfb_conv_train_dgrad_bnrelu(const float* gy, const float* w_bwd, 
 }
 
 // samples per CTA: large enough that the partial-sum traffic (groups x |gw|) stays small next to the FMA work
+// work units: samples, or bands of 8 rows for 32x32 inputs
+static int wgrad_units(int B, int h, int w) { return (h == 32 && w == 32) ? B * 4 : B; }
+
 static int wgrad_spc(int B, int Cin, int Cout, int h, int w) {
     const int pairs = ((Cin + 31) / 32) * ((Cout + 31) / 32);
+    B = wgrad_units(B, h, w);
     int spc = h * w >= 256 ? 2 : (h * w >= 64 ? 4 : 8);  // = a multiple of the samples staged per iteration
     const int fill = (B * pairs + kSMs * 2 - 1) / (kSMs * 2);  // never more than about two CTAs per SM in total
     if (spc < fill) spc = fill;
@@ -657,7 +704,7 @@ static int wgrad_spc(int B, int Cin, int Cout, int h, int w) {
 extern "C" long long nfb_conv_train_wgrad_scratch(int B, int Cin, int Cout, int h, int w, int ks) {
     if (B <= 0 || Cin <= 0 || Cout <= 0 || (ks != 1 && ks != 3)) return NFB_ERR_SHAPE;
     const int spc = wgrad_spc(B, Cin, Cout, h, w);
-    const long long groups = (B + spc - 1) / spc;
+    const long long groups = (wgrad_units(B, h, w) + spc - 1) / spc;
     return groups * (static_cast<long long>(Cout) * Cin * ks * ks + Cout);
 }
 
@@ -669,25 +716,27 @@ extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, 
     cudaStream_t st = as_stream(stream);
     const int pairs = ((Cin + 31) / 32) * ((Cout + 31) / 32);
     const int spc = wgrad_spc(B, Cin, Cout, h, w);
-    const int groups = (B + spc - 1) / spc;
+    const int units = wgrad_units(B, h, w);
+    const int groups = (units + spc - 1) / spc;
     dim3 grid(groups, pairs);
     int rc = NFB_ERR_UNSUPPORTED;
-#define NFB_WG(H_, W_, SPI_)                                                                                 \
+#define NFB_WG(H_, W_, SPI_, TILES_)                                                                         \
     do {                                                                                                     \
         constexpr size_t smem = sizeof(float) * 32 * ((SPI_) * (H_) * (W_) + 4 + (SPI_) * ((H_) + 2) * (W_) + 4); \
         static bool attr_set = false;                                                                        \
         if (!attr_set) {                                                                                     \
-            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3, SPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1, SPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3, SPI_, TILES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1, SPI_, TILES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
             attr_set = true;                                                                                 \
         }                                                                                                    \
-        if (ks == 3) wgrad_kernel<H_, W_, 3, SPI_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc); \
-        else wgrad_kernel<H_, W_, 1, SPI_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, B, spc);      \
+        if (ks == 3) wgrad_kernel<H_, W_, 3, SPI_, TILES_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, units, spc); \
+        else wgrad_kernel<H_, W_, 1, SPI_, TILES_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, units, spc); \
         rc = launch_status();                                                                                \
     } while (0)
-    if (h == 16 && w == 16) NFB_WG(16, 16, 1);
-    else if (h == 8 && w == 8) NFB_WG(8, 8, 4);
-    else if (h == 4 && w == 4) NFB_WG(4, 4, 8);
+    if (h == 16 && w == 16) NFB_WG(16, 16, 1, 1);
+    else if (h == 8 && w == 8) NFB_WG(8, 8, 4, 1);
+    else if (h == 4 && w == 4) NFB_WG(4, 4, 8, 1);
+    else if (h == 32 && w == 32) NFB_WG(8, 32, 1, 4);
 #undef NFB_WG
     if (rc != NFB_OK) return rc;
     const int n_w = Cout * Cin * ks * ks;

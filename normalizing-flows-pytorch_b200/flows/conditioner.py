@@ -2,7 +2,7 @@
 
 ``MLP`` / ``ConvNet`` (RealNVP, Glow): in_block.0 -> 2 residual blocks (BN, ReLU, WN-layer, BN, ReLU, WN-layer)
 -> out_block (BN, ReLU, WN-layer).  Eval mode without autograd: ONE fused kernel over folded weights.  Train mode (batch
-statistics, modules.py:349-352): ``ConvNet`` at 16x16 / 8x8 / 4x4 and ``MLP`` (batch a multiple of 16) run layer by layer
+statistics, modules.py:349-352): ``ConvNet`` at 32x32 / 16x16 / 8x8 / 4x4 and ``MLP`` (batch a multiple of 16) run layer by layer
 on libnfb200 kernels, forward and backward (``conditioner_train.py``); other shapes and eval-mode-with-gradients use
 cuDNN / cuBLAS ops under torch autograd (``_forward_autograd``).
 """
@@ -169,7 +169,7 @@ class _ResNetConditioner(nn.Module):
             return F.conv2d(x, w, wn.module.bias, 1, (w.size(2) - 1) // 2)
         return F.linear(x, w, wn.module.bias)
 
-    # train mode on libnfb200 kernels (ConvNet at 16x16 / 8x8 / 4x4, MLP); False = cuDNN / cuBLAS ops under torch autograd
+    # train mode on libnfb200 kernels (ConvNet at 32x32 / 16x16 / 8x8 / 4x4, MLP); False = cuDNN / cuBLAS ops under torch autograd
     native_train = True
 
     def _forward_native_train(self, x):

@@ -19,7 +19,7 @@ from torch.autograd.function import once_differentiable
 
 from .. import _lib as L
 
-SUPPORTED_HW = ((16, 16), (8, 8), (4, 4))
+SUPPORTED_HW = ((32, 32), (16, 16), (8, 8), (4, 4))  # 32x32 (first level of a 64x64 Glow) runs as four 8 x 32 bands
 F32 = 32  # base_filters
 
 

@@ -355,14 +355,16 @@ def test_graphed_train_step_matches_eager():
 
 
 @pytest.mark.parametrize('cin,cout,hw,B', [(6, 12, 16, 8), (24, 48, 8, 8), (96, 192, 4, 6), (6, 12, 4, 5), (384, 768, 4, 3),
-                                           (3, 6, 8, 7), (40, 70, 16, 4)])
+                                           (3, 6, 8, 7), (40, 70, 16, 3), (6, 12, 32, 4), (40, 24, 32, 2)])
 def test_native_train_conditioner_vs_library(cin, cout, hw, B):
     """Train-mode ConvNet on the libnfb200 layer kernels (csrc/conditioner_train.cu) against the same module run through
     cuDNN / cuBLAS ops under torch autograd: output, input gradient, every parameter gradient, running statistics.
 
-    (Seeded data: ReLU is not differentiable at 0, so a pre-activation within fp32 rounding of zero -- about 1 in 1e7
-    elements -- can take a different branch in two correct implementations and shift the gradients around it; the case
-    (40, 70, 16, B=3) of an earlier version of this test hit one at 4e-7 and was moved to B=4.)"""
+    ReLU is not differentiable at 0: a pre-activation within rounding of zero (observed at |y| = 4e-7) takes a different
+    branch in two correct implementations and shifts the gradients in the receptive field around it by ~1e-2.  cuDNN's
+    FFT / Winograd algorithms round at ~1e-5, which makes such flips common against the library path (2 of 3 draws at
+    32x32), so the GRADIENTS are checked against the fp64 CPU oracle (flip window ~1e-7) on three independent data draws,
+    one of which may deviate; outputs and running statistics must agree with the library path on all three."""
     F = nfb().flows
     torch.manual_seed(1)
     net = F.ConvNet(cin, cout)
@@ -375,34 +377,44 @@ def test_native_train_conditioner_vs_library(cin, cout, hw, B):
                 p.add_(0.1 * torch.randn(p.shape, generator=gen))
     net.to(DEV).train()
     snap = {k: v.clone() for k, v in net.state_dict().items()}
-    x = torch.randn(B, cin, hw, hw, generator=gen).to(DEV)
-    R = torch.randn(B, cout, hw, hw, generator=gen).to(DEV)
-    res = []
-    for native in (True, False):
-        net.native_train = native
-        net.load_state_dict(snap)
-        net.zero_grad(set_to_none=True)
-        xx = x.clone().requires_grad_(True)
-        n0 = nfb()._lib.launch_count()
-        out = net(xx)
-        (out * R).sum().backward()
-        launches = nfb()._lib.launch_count() - n0
-        assert (launches >= 20) == native, launches  # the native path really is made of libnfb200 launches
-        res.append((out.detach(), xx.grad, {k: p.grad.clone() for k, p in net.named_parameters()},
-                    {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k}))
-    (o1, g1, p1, s1), (o0, g0, p0, s0) = res
-    GC.grad_close(o1, o0, 2e-5, 'out')
-    floor = GC.grad_floor(p0)
-    GC.grad_close(g1, g0, 2e-4, 'gx', floor)
-    for k in p0:
-        GC.grad_close(p1[k], p0[k], 2e-4, k, floor)
-    for k in s0:
-        GC.grad_close(s1[k].float(), s0[k].float(), 2e-5, k)
+    deviating = []
+    for draw in range(3):
+        x = torch.randn(B, cin, hw, hw, generator=gen).to(DEV)
+        R = torch.randn(B, cout, hw, hw, generator=gen).to(DEV)
+        res = []
+        for native in (True, False):
+            net.native_train = native
+            net.load_state_dict(snap)
+            net.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_(True)
+            n0 = nfb()._lib.launch_count()
+            out = net(xx)
+            (out * R).sum().backward()
+            launches = nfb()._lib.launch_count() - n0
+            assert (launches >= 20) == native, launches  # the native path really is made of libnfb200 launches
+            res.append((out.detach(), xx.grad, {k: p.grad.clone() for k, p in net.named_parameters()},
+                        {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k}))
+        (o1, g1, p1, s1), (o0, g0, p0, s0) = res
+        GC.grad_close(o1, o0, 2e-5, 'out')
+        for k in s0:
+            GC.grad_close(s1[k].float(), s0[k].float(), 2e-5, k)
+        leaves = GC.leaf_state({k: v.cpu() for k, v in snap.items()}, torch.float64)
+        xd = x.cpu().double().requires_grad_(True)
+        (O.resnet_conditioner(leaves, '', xd, True) * R.cpu().double()).sum().backward()
+        floor = GC.grad_floor(p0)
+        try:
+            GC.grad_close(g1, xd.grad, 2e-4, 'gx', floor)
+            for k in p0:
+                GC.grad_close(p1[k], leaves[k].grad, 2e-4, k, floor)
+        except AssertionError as e:
+            deviating.append('draw %d: %s' % (draw, e))
+    assert len(deviating) <= 1, deviating
 
 
 @pytest.mark.parametrize('cin,cout,hw,ks,B', [(40, 32, 16, 3, 3), (32, 40, 16, 3, 3), (32, 70, 16, 1, 3), (70, 32, 16, 1, 3),
                                               (32, 32, 16, 3, 5), (6, 32, 8, 3, 9), (32, 6, 8, 3, 9), (96, 32, 4, 3, 7),
-                                              (32, 192, 4, 1, 7), (192, 32, 4, 1, 7), (32, 32, 4, 3, 2)])
+                                              (32, 192, 4, 1, 7), (192, 32, 4, 1, 7), (32, 32, 4, 3, 2),
+                                              (6, 32, 32, 3, 3), (32, 40, 32, 3, 2), (32, 12, 32, 1, 2), (70, 32, 32, 1, 3)])
 def test_train_conv_kernels_vs_torch(cin, cout, hw, ks, B):
     """The layer kernels of csrc/conditioner_train.cu one by one against torch (fp64 on the CPU): WeightNorm + packing,
     convolution (+bias, +skip, +moments), its data gradient through the flipped / transposed pack, weight / bias gradient."""
