@@ -160,7 +160,16 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
     const int n_ic = (A.Cin + 31) >> 5, n_oc = (A.Cout + 31) >> 5;
     constexpr int HWv = H * W / 4;
 
-    for (int i = t; i < kF * CHS; i += NT) bufA[i] = 0.f;  // zero halo rows (and channels past Cin)
+    if (TILES == 1) {  // zero halo rows above / below every sample (banded images load theirs); channels past Cin are never read
+        for (int i = t; i < kF * S * 2 * (W / 4); i += NT) {
+            const int ci = i / (S * 2 * (W / 4));
+            int rem = i - ci * (S * 2 * (W / 4));
+            const int ss = rem / (2 * (W / 4));
+            rem -= ss * (2 * (W / 4));
+            const int row = rem / (W / 4) ? H + 1 : 0, xv = rem % (W / 4);
+            st4(bufA + ci * CHS + ss * (H + 2) * W + row * W + 4 * xv, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
     for (int oc = 0; oc < n_oc; ++oc) {
         float acc[OCT][4];
 #pragma unroll
@@ -175,10 +184,11 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
                     const int rem = i - ci * ((H + 2) * RWv);
                     const int rr = rem / RWv, xv = rem - rr * RWv;
                     const int gr = r0 + rr - 1, ch = ic * 32 + ci;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* dst = bufA + ci * CHS + rr * W + 4 * xv;
                     if (valid && ch < A.Cin && gr >= 0 && gr < HF)
-                        v = ldg4(A.in + ((static_cast<size_t>(b) * A.Cin + ch) * HF + gr) * W + 4 * xv);
-                    st4(bufA + ci * CHS + rr * W + 4 * xv, v);
+                        cp_async16(dst, A.in + ((static_cast<size_t>(b) * A.Cin + ch) * HF + gr) * W + 4 * xv);
+                    else
+                        st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             } else if (n_ic > 1 || oc == 0) {
                 // input chunk: channels [32 ic, 32 ic + 32) of the CTA's S samples, float4 per thread
@@ -188,13 +198,17 @@ __global__ void __launch_bounds__(NT) conv_layer_kernel(ConvArgs A) {
                     const int ss = rem / HWv;
                     rem -= ss * HWv;
                     const int bb = blockIdx.x * S + ss, ch = ic * 32 + ci;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bb < A.B && ch < A.Cin) v = ldg4(A.in + (static_cast<size_t>(bb) * A.Cin + ch) * (H * W) + 4 * rem);
-                    st4(bufA + ci * CHS + ss * (H + 2) * W + W + 4 * rem, v);
+                    // asynchronous copies: all of a thread's requests are in flight together (no register staging);
+                    // samples past the batch and channels past Cin are never consumed
+                    if (bb < A.B && ch < A.Cin)
+                        cp_async16(bufA + ci * CHS + ss * (H + 2) * W + W + 4 * rem,
+                                   A.in + (static_cast<size_t>(bb) * A.Cin + ch) * (H * W) + 4 * rem);
                 }
             }
             const float* wsrc = A.w + (static_cast<size_t>(oc) * n_ic + ic) * (32 * KK * 32);
-            for (int i = t * 4; i < 32 * KK * 32; i += NT * 4) st4(wsm + i, ldg4(wsrc + i));
+            for (int i = t * 4; i < 32 * KK * 32; i += NT * 4) cp_async16(wsm + i, wsrc + i);
+            cp_async_commit();
+            cp_async_wait_all();
             __syncthreads();
             const int CI = (A.Cin - ic * 32) < kF ? (A.Cin - ic * 32) : kF;
             if (KS == 3) {
