@@ -36,6 +36,33 @@ def test_argument_errors_are_negative_codes_without_touching_the_gpu():
         L.check(L.ERR_SHAPE)
 
 
+def test_training_entry_points_validate_arguments_on_the_host():
+    """The gradient / train-conditioner entry points reject bad arguments before any launch, and the scratch-size helpers
+    are plain host arithmetic (no GPU needed)."""
+    import nfb200._lib as L
+    lib = L.lib()
+    fake = ctypes.c_void_p(256)
+    assert lib.nfb_affine_coupling_bwd(None, fake, fake, fake, fake, fake, fake, fake, fake, fake, fake, 4, 3, 4, 4,
+                                       L.SPLIT_CHECKER, 0, None) == L.ERR_NULL
+    assert lib.nfb_affine_coupling_bwd(fake, fake, fake, fake, fake, fake, fake, fake, fake, fake, fake, 4, 3, 5, 5,
+                                       L.SPLIT_CHECKER, 0, None) == L.ERR_SPLIT
+    assert lib.nfb_rqs_coupling_bwd(fake, fake, fake, fake, fake, fake, 4, 4, 1, 1, L.SPLIT_1D, 0, 1, 3.0, None) == L.ERR_SHAPE
+    assert lib.nfb_mixlog_coupling_bwd(fake, fake, fake, fake, fake, fake, fake, fake, fake, fake, fake, 4, 4, 1, 1,
+                                       L.SPLIT_1D, 0, 99, None) == L.ERR_UNSUPPORTED
+    assert lib.nfb_conv_train(fake, fake, None, None, fake, None, 0, 4, 32, 32, 5, 5, 3, None) == L.ERR_UNSUPPORTED
+    assert lib.nfb_conv_train(fake, fake, None, None, fake, None, 0, 4, 32, 32, 16, 16, 2, None) == L.ERR_SHAPE
+    assert lib.nfb_rows_to_planes(fake, fake, 100, 8, 64, None) == L.ERR_SHAPE  # 100 rows are not whole planes of 64
+    assert lib.nfb_wn_pack_train_multi(fake, fake, 0, 1e-5, None) == L.ERR_SHAPE
+    # sample groups x (|gw| + |gb|): B = 256 at 16x16 -> 2 samples per CTA -> 128 groups
+    assert lib.nfb_conv_train_wgrad_scratch(256, 32, 32, 16, 16, 3) == 128 * (32 * 32 * 9 + 32)
+    # 32x32: 4 bands per sample = 1024 units, 4 per CTA (about two CTAs per SM in total) -> 256 groups
+    assert lib.nfb_conv_train_wgrad_scratch(256, 32, 32, 32, 32, 3) == 256 * (32 * 32 * 9 + 32)
+    assert lib.nfb_invconv1x1_wgrad_scratch(256, 48, 64) == 128 * 48 * 48
+    ptrs = (ctypes.c_void_p * 15)(*[256] * 15)
+    assert lib.nfb_flowpp_mlp_fwd(ptrs, fake, fake, 8, 4, L.SPLIT_1D, 0, 2, 100000, None) == L.ERR_UNSUPPORTED
+    assert lib.nfb_flowpp_mlp_fwd(ptrs, fake, fake, 8, 5, L.SPLIT_1D, 0, 2, 14, None) == L.ERR_SHAPE
+
+
 def test_no_cpu_fallback():
     import nfb200
     with pytest.raises(RuntimeError, match='CUDA'):
