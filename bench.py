@@ -382,7 +382,8 @@ def run_nfb200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
         # ---- CUDA graphs of one step: `streams` batches in flight, one graph + static buffers per stream ----------
-        n_str = max(1, args.streams)
+        # N > 1: every lane issues its own all-reduce; 3 lanes is the configuration validated at N = 2 and N = 8
+        n_str = max(1, args.streams if world == 1 else min(args.streams, 3))
         lanes = []
         for k in range(n_str):
             st = torch.cuda.Stream()
