@@ -87,7 +87,7 @@ def test_model_gradients_vs_reference_golden(name):
     rows, total = net.nll(src['x'].to(DEV))
     loss = rows.mean()  # main.py:85
     loss.backward()
-    assert abs(float(loss) - float(a['loss'])) <= 1e-5 * abs(float(a['loss']))
+    assert abs(float(loss.detach()) - float(a['loss'])) <= 1e-5 * abs(float(a['loss']))
     s, cnt = total.tolist()
     assert abs(s / cnt - float(a['loss'])) <= 1e-5 * abs(float(a['loss']))
     got = named_grads(net)
@@ -304,7 +304,7 @@ def test_training_step_gradients_vs_oracle(cfg):
     loss.backward()
     lo, go = GC.oracle_model_grads(meta, sd, x, torch.float32, True, cfg.get('coupling'))
     _, g64 = GC.oracle_model_grads(meta, sd, x, torch.float64, True, cfg.get('coupling'))
-    assert abs(float(loss) - float(lo)) <= 2e-5 * abs(float(lo))
+    assert abs(float(loss.detach()) - float(lo)) <= 2e-5 * abs(float(lo))
     got = named_grads(net)
     buffers = dict(net.named_buffers())
     floor = GC.grad_floor(go)
