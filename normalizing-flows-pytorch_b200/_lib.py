@@ -53,6 +53,7 @@ _SIGNATURES = {
     'nfb_set_tuning': [_I, _I],
     'nfb_resnet_pack': [_P, _P, _I, _I, _I, _F, _F, _P],
     'nfb_convnet_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_convnet_affine_fwd': [_P] * 5 + [_I] * 6 + [_P],
     'nfb_glow_step_fwd': [_P] * 11 + [_I] * 6 + [_P],
     'nfb_pack_conv3x3': [_P, _P, _I, _I, _P],
     'nfb_flowpp_cond_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

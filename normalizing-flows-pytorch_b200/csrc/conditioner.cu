@@ -568,8 +568,8 @@ int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // runtime variant selection (nfb_set
 template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                             int h, int w, cudaStream_t st) {
-    if (g_tune[3] == 1) {  // tensor-core (tcgen05 3xTF32) path
-        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_layout(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, st);
+    if (g_tune[3] != 2) {  // default: tensor-core (tcgen05 3xTF32) kernel; 2 = FP32-FFMA kernels below (developer knob)
+        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_plan(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, st);
         if (rc != NFB_ERR_UNSUPPORTED) return rc;
     }
 #define NFB_CONV(H_, W_, NT_, OCT_) return launch_convnet<H_, W_, NT_, OCT_, MODE>(zsrc, out, pk, g, Cin, Cout, B, st)
@@ -695,7 +695,7 @@ extern "C" int nfb_set_tuning(int key, int value) {
 extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
     if (!conv) return pack_layout(in_ch, out_ch, 1).total;
-    const TcLayout T = tc_layout(in_ch, out_ch);  // FFMA section followed by the tensor-core (3xTF32) section
+    const TcPlan T = tc_plan(in_ch, out_ch);  // FFMA section followed by the tensor-core (3xTF32) section
     return T.base + T.total;
 }
 
@@ -734,7 +734,7 @@ extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, 
     if ((rc = bn(4, packed + L.bnO))) return rc;
     if ((rc = wn(5, -1, packed + L.wout, packed + L.bout, out_ch, kF, CoutPad))) return rc;
     if (!conv) return NFB_OK;
-    return pack_tc_launch(packed, packed + tc_layout(in_ch, out_ch).base, in_ch, out_ch, st);
+    return pack_tc_launch(packed, packed + tc_plan(in_ch, out_ch).base, in_ch, out_ch, st);
 }
 
 extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
@@ -754,6 +754,19 @@ extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float*
     if (mode == NFB_SPLIT_CHECKER) return dispatch_convnet<NFB_SPLIT_CHECKER>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
     if (mode == NFB_SPLIT_CHANNEL) return dispatch_convnet<NFB_SPLIT_CHANNEL>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
     return NFB_ERR_SHAPE;
+}
+
+extern "C" int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale,
+                                      const float* s_bias, int B, int C, int H, int W, int mode, int odd,
+                                      nfb_stream_t stream) {
+    if (!z || !ldj || !packed || !s_log_scale || !s_bias) return NFB_ERR_NULL;
+    SplitGeom g;
+    const int rc = make_geom(g, B, C, H, W, mode, odd);
+    if (rc != NFB_OK) return rc;
+    if (mode != NFB_SPLIT_CHECKER && mode != NFB_SPLIT_CHANNEL) return NFB_ERR_UNSUPPORTED;
+    if (g_tune[3] == 2) return NFB_ERR_UNSUPPORTED;
+    return convnet_affine_tc_dispatch(z, ldj, packed + tc_plan(g.c0, 2 * g.c0).base, g, mode, g.c0, 2 * g.c0, B, s_log_scale,
+                                      s_bias, as_stream(stream));
 }
 
 template <int MODE>

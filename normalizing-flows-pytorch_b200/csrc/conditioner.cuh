@@ -95,34 +95,66 @@ __device__ __forceinline__ void conv3x3_acc(float (&acc)[OCT][4], const float* _
 }
 
 // ---- tensor-core (tcgen05, 3xTF32) section of the packed buffer, appended after the FFMA section -----------------
-// consts: b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO  (11 x 32 floats) + bout (CoutPad); b1' has the second
-// BatchNorm of the block folded in (like the weights of its conv).  stage i (n_in in-conv passes, then 4 mid layers): hi[9216],
-// lo[9216] floats, B operand K-major no-swizzle: element (n, tap, ci) at ((tap*8 + ci/4)*32 + n)*4 + ci%4.
-// out: per chunk of 32 output channels 1024 floats, (n, ci) at ((ci/4)*32 + n)*4 + ci%4; hi section then lo section.
-constexpr int kTcStage = 9 * 8 * 32 * 4;  // 9216 floats per hi (or lo) half of a 3x3 stage
-struct TcLayout {
-    int base;     // offset of the TC section inside the packed buffer
-    int consts, stage0, out_hi, out_lo, total;  // offsets relative to `base`
-    int n_in, n_chunks, cout_pad;
+// All offsets in floats relative to `base`; every block is the exact shared-memory image the kernel's TMA copies fetch.
+//   consts   b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO   (11 x 32 floats; b1' has the second BatchNorm of the
+//            block folded in, like the weights of its conv)
+//   obias_*  output-layer bias by column, generic channel order / fused (t | s_raw) order
+//   in0      in-conv passes of <= 32 input channels, mid0: the four 32->32 layers.  One 3x3 stage =
+//            [tap 9][k-step j][k4 2][n 64: w_hi(co) | w_lo(co)][4 ci], ci = 32*pass + 8j + 4*k4 + q: the UMMA K-major
+//            no-swizzle layout of a (64 x 8) B tile per k-step (LBO 1024 B, SBO 128 B), 2048 B each
+//   out*     output layer (1x1) in chunks of NW columns: [j 4][k4 2][n 2NW: hi | lo][4 ci]; fused order: columns
+//            [0, NW/2) = t, [NW/2, NW) = s_raw of the same NW/2 transformed channels (coupling.py:106-107)
+struct TcPlan {
+    int base;
+    int n_in, nj_last;       // in-conv passes; k-steps per tap of the last pass (the others have 4)
+    int NWg, nqg, NWf, nqf;  // output layer: columns per chunk (multiple of 16, <= 128) and chunks, generic / fused
+    int consts, obias_g, obias_f, in0, mid0, outg, outf, total;
 };
-__host__ __device__ inline TcLayout tc_layout(int Cin, int Cout) {
-    TcLayout T;
-    T.base = (pack_layout(Cin, Cout, 9).total + 31) & ~31;
-    T.n_in = (Cin + kF - 1) / kF;
-    T.cout_pad = (Cout + 31) & ~31;
-    T.n_chunks = T.cout_pad / 32;
+constexpr int kTcStageFloats = 9 * 4 * 512;  // one full 3x3 stage (72 KB)
+__host__ __device__ inline TcPlan tc_plan(int Cin, int Cout) {
+    TcPlan P;
+    P.base = (pack_layout(Cin, Cout, 9).total + 31) & ~31;
+    P.n_in = (Cin + kF - 1) / kF;
+    const int last = Cin - (P.n_in - 1) * kF;
+    P.nj_last = ((last + 7) & ~7) / 8;
+    P.nqg = (Cout + 127) / 128;
+    P.NWg = (((Cout + P.nqg - 1) / P.nqg) + 15) & ~15;
+    if (Cout % 2 == 0) {
+        const int c0 = Cout / 2;
+        P.nqf = (((c0 + 7) & ~7) + 63) / 64;
+        P.NWf = 2 * ((((c0 + P.nqf - 1) / P.nqf) + 7) & ~7);
+    } else {
+        P.nqf = 0;
+        P.NWf = 0;
+    }
     int o = 0;
-    T.consts = o; o += 352 + T.cout_pad;
-    T.stage0 = o; o += (T.n_in + 4) * 2 * kTcStage;
-    T.out_hi = o; o += T.n_chunks * 1024;
-    T.out_lo = o; o += T.n_chunks * 1024;
-    T.total = o;
-    return T;
+    P.consts = o; o += 352;
+    P.obias_g = o; o += P.nqg * P.NWg;
+    P.obias_f = o; o += P.nqf * P.NWf;
+    P.in0 = o; o += (P.n_in - 1) * kTcStageFloats + 9 * P.nj_last * 512;
+    P.mid0 = o; o += 4 * kTcStageFloats;
+    P.outg = o; o += P.nqg * 64 * P.NWg;
+    P.outf = o; o += P.nqf * 64 * P.NWf;
+    P.total = o;
+    return P;
+}
+// output channel behind column `col` of chunk `q` (-1: padding)
+__host__ __device__ inline int tc_out_channel(bool fused, int q, int col, int NW, int c0, int Cout) {
+    if (!fused) {
+        const int oc = q * NW + col;
+        return oc < Cout ? oc : -1;
+    }
+    const int PC = NW / 2;
+    const int m = q * PC + (col < PC ? col : col - PC);
+    if (m >= c0) return -1;
+    return col < PC ? m : c0 + m;
 }
 
 extern int g_tune[8];
 int convnet_tc_dispatch(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
                         int B, int h, int w, cudaStream_t st);
+int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout, int B,
+                               const float* sa, const float* sb, cudaStream_t st);
 int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace nfb

@@ -1,82 +1,186 @@
-// conditioner_tc.cu -- the ConvNet conditioner (modules.py:416-438) on the 5th-generation tensor cores.
+// conditioner_tc.cu -- the ConvNet conditioner (modules.py:416-438, weight_norm.py:35-45) on the 5th-generation tensor
+// cores, optionally fused with AffineCoupling._transform (coupling.py:104-112) so that (t, s) never leave the SM.
 //
-// Every 3x3 / 1x1 layer is an implicit GEMM issued with tcgen05.mma (kind::tf32, M=128, N=32, K=8) by ONE thread,
-// accumulators in TMEM, operands in shared memory.  Precision: single-pass TF32 misses the 1e-5 bits/dim bar
-// (SURVEY.md F8), so every product is error-compensated ("3xTF32"): x = x_hi + x_lo with x_hi the top 19 bits,
-//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (fp32 accumulation in TMEM; the dropped a_lo*b_lo is ~2^-22 relative).
+// Arithmetic: every 3x3 / 1x1 layer is an implicit GEMM issued with tcgen05.mma (kind::tf32, M = 128 positions) by ONE
+// thread, accumulators in TMEM.  Single-pass TF32 misses the 1e-5 bits/dim bar, so every product is
+// error-compensated ("3xTF32"): x = x_hi + x_lo, x_hi = tf32(x) (round to nearest), x_lo = tf32(x - x_hi),
+//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi            (the dropped a_lo*b_lo is ~2^-24 relative).
+// The GEMM is skinny (N = 32 output channels) and in SS mode every MMA re-reads its 4 KB A tile from shared memory,
+// so the operand B is N-CONCATENATED: rows [w_hi | w_lo] give a_hi*b_hi and a_hi*b_lo from ONE A read (N = 64), and
+// a_lo*b_hi is a second MMA (N = 32) into the compensation columns: 2 A reads per k-step instead of 3.
 //
-// "Flat shift" implicit GEMM: the CTA keeps the zero-padded activations of its S samples as ONE flat sequence of
-// positions (padded image (H+2)x(W+2), samples back to back, G = W+3 guard positions at both ends), stored K-major
-// WITHOUT swizzle as [ci/4][position][4 ci] -- the canonical UMMA layout ((8,m),2):((1,SBO),LBO) in 16-byte units with
-// SBO = 8 positions and LBO = one channel-chunk plane.  A 3x3 tap is then just a row offset (ky-1)*(W+2)+(kx-1) added
-// to the A descriptor's start address: the same buffer feeds all nine taps, no im2col, no shifted copies.  Outputs are
-// computed for every flat position (padding positions included; 128 per tile) and the epilogue writes zeros back to
-// the padding positions, which keeps the halo intact for the next layer.
+// Implicit GEMM without padding or im2col ("flat shift + lane masks"): a tile is 128 consecutive positions of the flat
+// (sample, y, x) sequence, stored K-major without swizzle as [ci/4][position][4 ci]; a 3x3 tap is a row offset
+// (dy*W + dx) in the A descriptor's start address, and the rows whose tap falls outside the image are switched off
+// with the instruction's disable-output-lane mask.  M utilisation is 100 % (16x16: 2 tiles per sample; 8x8: 2 samples
+// per tile; 4x4: 8 samples per tile).
 //
-// Accumulation: the tensor core adds into its fp32 accumulator with truncation, so a long chain of MMAs into one
-// accumulator drifts by ~(number of MMAs) x 2^-24 (measured: 1.2e-5 with all 108 MMAs of a layer in one chain).  Each
-// layer therefore uses FOUR TMEM accumulators per tile: one per kernel row for the a_hi*b_hi products (12 MMAs each) and
-// one for the small compensation terms; the epilogue sums them in registers with round-to-nearest.  The residual stream
-// lives in registers (the thread that owns TMEM lane m owns flat position 128t+m in every layer; one CTA per SM leaves
-// 255 registers per thread).
-// Per stage: [thread 0 issues 108*T MMAs] -> tcgen05.commit -> mbarrier -> [all 4 warps: tcgen05.ld their 32 TMEM lanes,
-// bias/BN/ReLU, hi/lo split, st.shared into the activation planes] while cp.async streams the next stage's weights.
+// Accumulation: the tensor core adds into the fp32 accumulator with truncation, so a long MMA chain drifts by
+// ~(chain length) x 2^-24.  The k-steps of a layer are therefore spread over G accumulator groups (default 3: <= 13
+// chained MMAs), each [main 32 | compensation 32] columns, started by an unmasked centre-tap MMA with accumulate = 0
+// and summed by the epilogue with round-to-nearest adds.
+//
+// Roles (320 threads, one persistent CTA per SM, units = groups of samples round-robin over the grid):
+//   warp 9   TMA producer: streams the weight stages (<= 72 KB each: [tap][k-step][w_hi|w_lo], the exact shared-memory
+//            image, packed once per weight update) with cp.async.bulk into a 2-slot ring, mbarrier complete_tx.
+//   warp 8   MMA issuer (one lane): waits weights-full + activations-ready, issues tcgen05.mma, tcgen05.commit ->
+//            accumulators-done / weights-empty / halo-free mbarriers.
+//   warps 0-7 epilogue: tcgen05.ld -> bias / BatchNorm / ReLU / residual (registers) -> hi/lo split -> st.shared into
+//            the activation planes of the NEXT layer (in place) -> activations-ready; gather of z1 from z with the
+//            coupling's split addressing; final layer: affine coupling on z0 (in place on z) + per-sample log-det, or
+//            the plain params store.
+// 16x16: the two tiles of a sample overlap (epilogue of one under the MMAs of the other); the in-place activation
+// update is ordered by a "halo-free" commit after the second tile's dy = -1 taps.
+#include <utility>
+
 #include "conditioner.cuh"
 
 namespace nfb {
 
+namespace {
+
+template <int V>
+using IC = std::integral_constant<int, V>;
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+    (f(IC<Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // bounded: a lost arrival must trap (cudaErrorLaunchFailure), never hang the GPU
-    uint32_t done = 0;
-    for (int it = 0; it < (1 << 22) && !done; ++it) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded (4 s of wall clock): a lost arrival must trap (cudaErrorLaunchFailure), never hang the GPU
+    if (mbar_try(bar, parity)) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it)
+            if (mbar_try(bar, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
     }
-    if (!done) __trap();
+}
+// TMA (bulk async copy engine): global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// true in exactly one lane of the (converged) warp; the compiler treats the guarded region as single-lane uniform code
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// D[tmem] (+)= A[smem] * B[smem]; rows whose bit is set in the 128-bit mask keep their old accumulator value
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
         : "memory");
 }
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 32 consecutive TMEM columns of this thread's lane -> registers
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+// N consecutive TMEM columns of this thread's lane -> registers (load + wait in one statement: the registers are
+// defined when the statement retires)
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        : "r"(taddr)
+        : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -91,273 +195,596 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                              // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
 
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128 (mma_sm100_desc.hpp bit layout)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N as given (mma_sm100_desc.hpp bit layout)
+__host__ __device__ constexpr uint32_t idesc_n(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
-template <int H, int W, int S>
-struct TcGeom {
-    static constexpr int Wp = W + 2, Hp = H + 2, Lp = Hp * Wp, PTOT = S * Lp;
-    static constexpr int T = (PTOT + 127) / 128;  // M tiles
-    static constexpr int G = Wp + 1;              // guard positions on both ends
-    static constexpr int PBUF = T * 128 + 2 * G;  // positions per channel-chunk plane
-    static constexpr int CS = PBUF * 4;           // floats per plane
-    static constexpr int TMEM_COLS = (4 * T * 32 <= 128) ? 128 : (4 * T * 32 <= 256) ? 256 : 512;  // 4 accumulators x T tiles
-    static_assert(4 * T * 32 <= 512, "tile count exceeds TMEM");
-    static constexpr size_t SMEM = (static_cast<size_t>(16) * CS + 2 * kTcStage + 1152 + 8) * sizeof(float);
+// bit l of word wd set <=> lane 32*wd + l of tile t is a position whose tap (dy, dx) falls outside its image
+template <int H, int W>
+__host__ __device__ constexpr uint32_t edge_mask(int t, int dy, int dx, int wd) {
+    uint32_t m = 0;
+    for (int l = 0; l < 32; ++l) {
+        const int p = t * 128 + wd * 32 + l;
+        const int pix = p % (H * W);
+        const int y = pix / W, x = pix % W;
+        const bool off = (dy < 0 && y == 0) || (dy > 0 && y == H - 1) || (dx < 0 && x == 0) || (dx > 0 && x == W - 1);
+        if (off) m |= 1u << l;
+    }
+    return m;
+}
+
+// offset inside one sample (original layout of z) of channel m, pixel (i, j) of half `second` (0 = z0, 1 = z1)
+template <int MODE>
+__device__ __forceinline__ int half_elem_offset(const SplitGeom& g, int m, int second, int i, int j) {
+    const bool outer = (second ^ g.odd) == 0;
+    if (MODE == NFB_SPLIT_CHANNEL) return (m + (outer ? 0 : g.c0)) * g.HW + i * g.W + j;
+    const int k = outer ? (m < g.C ? m : m + 2 * g.C) : m + g.C;
+    return (k >> 2) * g.HW + (2 * i + ((k >> 1) & 1)) * g.W + 2 * j + (k & 1);
+}
+
+// developer timeline: when set (nfb_debug_timeline), CTA 0 records clock64() stamps: [role 0 = epilogue thread 0,
+// 1 = epilogue thread 128, 2 = MMA lane 0][event index] = (tag << 48) | (clock & 0xffffffffffff)
+__device__ unsigned long long* g_tl_buf = nullptr;
+constexpr int kTlEvents = 512;
+struct Timeline {
+    unsigned long long* p;
+    int n;
+    __device__ __forceinline__ void init(int role, bool on) {
+        p = (on && g_tl_buf) ? g_tl_buf + role * kTlEvents : nullptr;
+        n = 0;
+    }
+    __device__ __forceinline__ void stamp(int tag) {
+        if (p && n < kTlEvents) {
+            p[n++] = (static_cast<unsigned long long>(tag) << 48) | (static_cast<unsigned long long>(clock64()) & 0xffffffffffffull);
+        }
+    }
 };
 
-template <int H, int W, int S, int MODE>
-__global__ void __launch_bounds__(128, 1) convnet_tc_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
-                                                           const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
-                                                           int B, int dbg) {
-    using GM = TcGeom<H, W, S>;
-    constexpr int Wp = GM::Wp, Lp = GM::Lp, PTOT = GM::PTOT, T = GM::T, G = GM::G, PBUF = GM::PBUF, CS = GM::CS;
-    extern __shared__ __align__(128) float smem[];
-    float* actH = smem;                 // [8][PBUF][4]
-    float* actL = actH + 8 * CS;
-    float* wH = actL + 8 * CS;          // one stage of weights, hi then lo
-    float* wL = wH + kTcStage;
-    float* cst = wL + kTcStage;         // per-channel constants (352 + CoutPad <= 1152 floats)
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(cst + 1152);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+// tap issue order: centre first (its first Ge k-steps start the accumulator groups with accumulate = 0, unmasked);
+// tile 0 of a linked pair: dy = +1 taps last (they read tile 1's rows); tile 1: dy = -1 taps right after the centre
+// (they read tile 0's rows, which tile 0's epilogue overwrites once they are done)
+constexpr uint64_t kOrder0 = 0x876210534ull, kOrder1 = 0x876532104ull;
+constexpr int kSlotBytes = 9 * 4 * 2048;  // one 32->32 3x3 stage: [tap][k-step][2 x (64 rows x 16 B)]
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = 320;
+constexpr int kTileCols = 256;            // TMEM columns reserved per tile
 
-    const TcLayout TL = tc_layout(Cin, Cout);
-    const int tid = threadIdx.x, warp = tid >> 5;
+template <int H, int W>
+struct TcGeom {
+    static constexpr int HW = H * W;
+    static constexpr bool LINKED = HW > 128;            // a sample spans several tiles (16x16: 2)
+    static constexpr int T = LINKED ? HW / 128 : 1;     // tiles per unit
+    static constexpr int SPU = LINKED ? 1 : 128 / HW;   // samples per unit
+    static constexpr int CS = LINKED ? 1 : 2;           // epilogue warps per TMEM lane quarter of one tile
+    static constexpr int NCH = 32 / CS;                 // channels per epilogue thread
+    static constexpr int GUARD = (W + 1 + 3) & ~3;      // positions before / after the tiles (tap offsets reach there)
+    static constexpr int PB = 2 * GUARD + T * 128;      // positions per channel-chunk plane
+    static constexpr int PS = PB * 16;                  // bytes per plane
+    static constexpr int ACT_BYTES = 16 * PS;           // 8 hi planes + 8 lo planes
+    static_assert(T <= 2 && T * kTileCols <= 512, "unit exceeds TMEM");
+    static_assert(HW == 256 || 128 % HW == 0, "tile must hold whole samples");
+};
 
-    auto load_weights = [&](const float* hi, const float* lo, int nfloats) {
-        for (int i = tid * 4; i < nfloats; i += 128 * 4) { cp_async16(wH + i, hi + i); cp_async16(wL + i, lo + i); }
-        cp_async_commit();
-    };
-    auto stage_ptr = [&](int s) { return pk + TL.stage0 + static_cast<size_t>(s) * 2 * kTcStage; };
+}  // namespace
 
-    // ---- prologue: first weights in flight, zero the activation planes, constants, barrier, TMEM -----------------
-    load_weights(stage_ptr(0), stage_ptr(0) + kTcStage, kTcStage);
-    for (int i = tid * 4; i < 16 * CS; i += 128 * 4) st4(smem + i, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int i = tid; i < 352 + TL.cout_pad && i < 1152; i += 128) cst[i] = __ldg(pk + TL.consts + i);
-    if (tid == 0) mbar_init(mbar, 1);
-    if (warp == 0) {
+// =====================================================================================================================
+// the kernel
+// =====================================================================================================================
+template <int H, int W, int MODE, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 1)
+convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
+                  int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, int G, int dbg) {
+    using GM = TcGeom<H, W>;
+    constexpr int HW = GM::HW, T = GM::T, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD, PB = GM::PB,
+                  PS = GM::PS;
+    constexpr bool LINKED = GM::LINKED;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* act = smem_raw;                              // [16 planes][PB][16 B]
+    unsigned char* ring = smem_raw + GM::ACT_BYTES;             // 2 x kSlotBytes
+    float* cst = reinterpret_cast<float*>(ring + 2 * kSlotBytes);
+
+    const TcPlan P = tc_plan(Cin, Cout);
+    const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cst + ((n_cst + 3) & ~3));
+    // barrier indices
+    constexpr int W_FULL = 0, W_EMPTY = 2, ACT_READY = 4, ACC_DONE = 6, WAR0 = 8, N_BARS = 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [8 warps][2]
+    uint4* mask_tab = reinterpret_cast<uint4*>(red + 16);        // [T][9 taps]: rows of the tile whose tap leaves the image
+    uint4* prog = mask_tab + 2 * 9;                              // [T][9 taps in issue order][mask, 4 k-steps]: see below
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NW = FUSED ? P.NWf : P.NWg, nq = FUSED ? P.nqf : P.nqg;
+    const int out_chunk_bytes = 256 * NW;
+    const int qps = kSlotBytes / out_chunk_bytes;               // out chunks per weight stage
+    const int n_out_stage = (nq + qps - 1) / qps;
+    const int n_stage = P.n_in + 4 + n_out_stage;
+    const int n_units = (B + SPU - 1) / SPU;
+
+    // ---- prologue: barriers, constants, TMEM ----------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(bar(W_FULL), 1); mbar_init(bar(W_FULL + 1), 1);
+        mbar_init(bar(W_EMPTY), 1); mbar_init(bar(W_EMPTY + 1), 1);
+        mbar_init(bar(ACT_READY), 128 * CS); mbar_init(bar(ACT_READY + 1), 128 * CS);
+        mbar_init(bar(ACC_DONE), 1); mbar_init(bar(ACC_DONE + 1), 1);
+        mbar_init(bar(WAR0), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < T * 9 * 4) {
+        const int t = tid / 36, tap = (tid % 36) / 4, wd = tid % 4;
+        reinterpret_cast<uint32_t*>(mask_tab)[tid] = edge_mask<H, W>(t, tap / 3 - 1, tap % 3 - 1, wd);
+    }
+    // Issue program of a 32->32 3x3 layer (4 k-steps per tap): the operands of all 72 k-steps are the same in every such
+    // layer, so they are tabulated once: per tap [lane mask | 4 x (A_hi descriptor lo word, A_lo descriptor lo word, B
+    // offset inside the weight slot, TMEM column | accumulate << 31)] in the order the MMA lane issues them.
+    if (tid < T * 36) {
+        const int t = tid / 36, i = (tid % 36) / 4, j = tid % 4;
+        const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
+        const int tap = static_cast<int>((order >> (4 * i)) & 15u);
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int Ge = G < 4 ? G : 4;
+        const int kc = 4 * i + j;
+        const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128 + dy * W + dx);
+        uint4 e;
+        e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+        e.y = (((smem_u32(act + 8 * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+        e.z = static_cast<uint32_t>((tap * 4 + j) * 128);
+        e.w = static_cast<uint32_t>(t * kTileCols + (kc % Ge) * 64) | (kc >= Ge ? 0x80000000u : 0u);
+        prog[(t * 9 + i) * 5 + 1 + j] = e;
+        if (j == 0)
+            prog[(t * 9 + i) * 5] = make_uint4(edge_mask<H, W>(t, dy, dx, 0), edge_mask<H, W>(t, dy, dx, 1),
+                                               edge_mask<H, W>(t, dy, dx, 2), edge_mask<H, W>(t, dy, dx, 3));
+    }
+    {
+        const float* src = pk + P.consts;
+        for (int i = tid; i < 352; i += kThreads) cst[i] = __ldg(src + i);
+        const float* ob = pk + (FUSED ? P.obias_f : P.obias_g);
+        for (int i = tid; i < nq * NW; i += kThreads) cst[352 + i] = __ldg(ob + i);
+    }
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(static_cast<uint32_t>(GM::TMEM_COLS)));
+                     "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    uint32_t phase = 0;
 
-    const uint64_t dAH = make_smem_desc(smem_u32(actH), PBUF * 16, 128), dAL = make_smem_desc(smem_u32(actL), PBUF * 16, 128);
-    const uint64_t dBH = make_smem_desc(smem_u32(wH), 512, 128), dBL = make_smem_desc(smem_u32(wL), 512, 128);
-
-    // TMEM accumulators of tile t: region r in {0,1,2} = kernel row ky (a_hi*b_hi), region 3 = compensation terms
-    auto region = [&](int r, int t) -> uint32_t { return tmem + static_cast<uint32_t>((r * T + t) * 32); };
-
-    // thread 0: all MMAs of one 3x3 (ntaps = 9) or 1x1 (ntaps = 1, centre tap) layer
-    auto issue_layer = [&](bool accumulate, int ksteps, int ntaps, uint32_t b_chunk_off) {
-        tc_fence_after();
-#pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-            uint32_t acc_c = accumulate ? 1u : 0u;
-#pragma unroll 1
-            for (int tap = 0; tap < ntaps; ++tap) {
-                const int ky = (ntaps == 9) ? tap / 3 : 0, kx = (ntaps == 9) ? tap % 3 : 0;
-                const int delta = (ntaps == 9) ? ((ky - 1) * Wp + (kx - 1)) : 0;
-                const uint32_t d_main = region(ky, t), d_comp = region(3, t);
-                uint32_t acc_m = (accumulate || kx != 0) ? 1u : 0u;
-#pragma unroll 1
-                for (int j = 0; j < ksteps; ++j) {
-                    const uint32_t a_off = static_cast<uint32_t>((2 * j) * PBUF + t * 128 + G + delta);  // 16-byte units
-                    const uint32_t b_off = b_chunk_off + static_cast<uint32_t>((tap * 8 + 2 * j) * 32);
-                    if (dbg & 1) continue;  // profiling knob: no tensor work
-                    mma_tf32(d_main, dAH + a_off, dBH + b_off, kIdesc, acc_m);
-                    if (dbg & 4) continue;  // profiling knob: single-pass TF32
-                    mma_tf32(d_comp, dAL + a_off, dBH + b_off, kIdesc, acc_c);
-                    mma_tf32(d_comp, dAH + a_off, dBL + b_off, kIdesc, 1u);
-                    acc_m = 1u;
-                    acc_c = 1u;
-                }
-            }
-        }
-        mma_commit(mbar);
-    };
-    // everyone: shared-memory writes -> visible to the tensor core, then one thread issues, everyone waits
-    auto run_layer = [&](bool accumulate, int ksteps, int ntaps, uint32_t b_chunk_off) {
-        cp_async_wait_all();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) issue_layer(accumulate, ksteps, ntaps, b_chunk_off);
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-        tc_fence_after();
-    };
-
-    // flat position -> (sample, y, x); true for an interior pixel of a valid sample
-    auto locate = [&](int p, int& b, int& y, int& x) -> bool {
-        if (p >= PTOT) return false;
-        const int s = p / Lp, r = p - s * Lp;
-        const int yy = r / Wp, xx = r - yy * Wp;
-        b = blockIdx.x * S + s;
-        y = yy - 1;
-        x = xx - 1;
-        return b < B && yy >= 1 && yy <= H && xx >= 1 && xx <= W;
-    };
-
-    // sum of the layer's accumulators for this thread's row of tile t (round-to-nearest adds in registers)
-    auto gather_acc = [&](int t, int nmain, float (&v)[32]) {
-        if (dbg & 2) nmain = 0;  // profiling knob: one TMEM load instead of four
-        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-        tmem_ld32(lane_base + region(3, t), v);
-        for (int r = 0; r < nmain; ++r) {
-            float u[32];
-            tmem_ld32(lane_base + region(r, t), u);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] += u[c];
-        }
-    };
-    // a[32] (already activated; zero outside the image) -> hi/lo planes at flat position p
-    auto store_act = [&](int p, const float (&a)[32]) {
-        float* ph = actH + (p + G) * 4;
-        float* pl = actL + (p + G) * 4;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { hi[q] = tf32_hi(a[c4 * 4 + q]); lo[q] = a[c4 * 4 + q] - hi[q]; }
-            st4(ph + c4 * CS, make_float4(hi[0], hi[1], hi[2], hi[3]));
-            st4(pl + c4 * CS, make_float4(lo[0], lo[1], lo[2], lo[3]));
-        }
-    };
-
-    // constants: b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO | bout
-    const float* c_b0 = cst;
-    auto c_blk = [&](int blk, int k) { return cst + 32 + blk * 128 + k * 32; };
-    const float* c_sO = cst + 288;
-    const float* c_tO = cst + 320;
-    const float* c_bout = cst + 352;
-
-    float xres[T][32];  // residual stream of this thread's rows
-
-    // ---- in conv: Cin -> 32 in passes of 32 input channels ---------------------------------------------------------
-    int stage = 0;
-    for (int c = 0; c < TL.n_in; ++c) {
-        const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
-        const int CI8 = (CI + 7) & ~7;
-        for (int p = tid; p < PTOT; p += 128) {
-            int b, y, x;
-            const bool in = locate(p, b, y, x);
-            for (int ci = 0; ci < CI8; ++ci) {
-                float v = 0.f;
-                if (in && ci < CI) {
-                    const int j = (c * kF + ci) * (H * W) + y * W + x;
-                    if (MODE < 0) v = __ldg(zsrc + static_cast<size_t>(b) * Cin * (H * W) + j);
-                    else v = __ldg(zsrc + static_cast<size_t>(b) * g.D + half_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, j, 1));
-                }
-                const float hi = tf32_hi(v);
-                const int o = (ci >> 2) * CS + (p + G) * 4 + (ci & 3);
-                actH[o] = hi;
-                actL[o] = v - hi;
-            }
-        }
-        run_layer(c > 0, CI8 / 8, 9, 0);
-        ++stage;
-        load_weights(stage_ptr(stage), stage_ptr(stage) + kTcStage, kTcStage);  // a next stage always exists here
-    }
-    // x = conv0 + b0;  a = relu(BN_a0(x))
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        float v[32], a[32];
-        gather_acc(t, 3, v);
-        int b, y, x;
-        const bool in = locate(t * 128 + tid, b, y, x);
-#pragma unroll
-        for (int ch = 0; ch < 32; ++ch) {
-            xres[t][ch] = v[ch] + c_b0[ch];
-            a[ch] = in ? fmaxf(fmaf(xres[t][ch], c_blk(0, 0)[ch], c_blk(0, 1)[ch]), 0.f) : 0.f;
-        }
-        store_act(t * 128 + tid, a);
-    }
-    tc_fence_before();
-
-    // ---- two residual blocks ------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-        run_layer(false, 4, 9, 0);  // conv1 (BN_b folded)
-        ++stage;
-        load_weights(stage_ptr(stage), stage_ptr(stage) + kTcStage, kTcStage);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            float v[32], a[32];
-            gather_acc(t, 3, v);
-            int b, y, x;
-            const bool in = locate(t * 128 + tid, b, y, x);
-#pragma unroll
-            for (int ch = 0; ch < 32; ++ch) a[ch] = in ? fmaxf(v[ch] + c_blk(blk, 2)[ch], 0.f) : 0.f;
-            store_act(t * 128 + tid, a);
-        }
-        tc_fence_before();
-        run_layer(false, 4, 9, 0);  // conv2
-        ++stage;
-        if (blk == 0) load_weights(stage_ptr(stage), stage_ptr(stage) + kTcStage, kTcStage);
-        const float* sN = blk == 0 ? c_blk(1, 0) : c_sO;  // the BatchNorm that consumes the updated residual stream
-        const float* tN = blk == 0 ? c_blk(1, 1) : c_tO;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            float v[32], a[32];
-            gather_acc(t, 3, v);
-            int b, y, x;
-            const bool in = locate(t * 128 + tid, b, y, x);
-#pragma unroll
-            for (int ch = 0; ch < 32; ++ch) {
-                xres[t][ch] += v[ch] + c_blk(blk, 3)[ch];
-                a[ch] = in ? fmaxf(fmaf(xres[t][ch], sN[ch], tN[ch]), 0.f) : 0.f;
-            }
-            store_act(t * 128 + tid, a);
-        }
-        tc_fence_before();
-    }
-
-    // ---- out block: conv1x1 32 -> Cout, 8 chunks of 32 output channels per weight stage ------------------------------
-    for (int c0 = 0; c0 < TL.n_chunks; c0 += 8) {
-        const int nc = (TL.n_chunks - c0) < 8 ? (TL.n_chunks - c0) : 8;
-        load_weights(pk + TL.out_hi + c0 * 1024, pk + TL.out_lo + c0 * 1024, nc * 1024);
-        for (int c = 0; c < nc; ++c) {
-            run_layer(false, 4, 1, static_cast<uint32_t>(c * 256));  // 1024 floats = 256 x 16 B per chunk
-#pragma unroll 1
-            for (int t = 0; t < T; ++t) {
-                float v[32];
-                gather_acc(t, 1, v);
-                int b, y, x;
-                if (locate(t * 128 + tid, b, y, x)) {
-#pragma unroll
-                    for (int o = 0; o < 32; ++o) {
-                        const int oc = (c0 + c) * 32 + o;
-                        if (oc < Cout) out[((static_cast<size_t>(b) * Cout + oc) * H + y) * W + x] = v[o] + c_bout[oc];
+    if (warp == 9) {
+        // =============================== TMA producer ================================================================
+        if (elect_one()) {
+            const unsigned char* pkb = reinterpret_cast<const unsigned char*>(pk);
+            uint32_t cnt = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                for (int s = 0; s < n_stage; ++s, ++cnt) {
+                    const uint32_t slot = cnt & 1u;
+                    mbar_wait(bar(W_EMPTY + slot), ((cnt >> 1) & 1u) ^ 1u);
+                    size_t off;
+                    uint32_t bytes;
+                    if (s < P.n_in) {
+                        off = static_cast<size_t>(P.in0) * 4 + static_cast<size_t>(s) * kSlotBytes;
+                        bytes = (s == P.n_in - 1) ? 9u * P.nj_last * 2048u : static_cast<uint32_t>(kSlotBytes);
+                    } else if (s < P.n_in + 4) {
+                        off = static_cast<size_t>(P.mid0) * 4 + static_cast<size_t>(s - P.n_in) * kSlotBytes;
+                        bytes = kSlotBytes;
+                    } else {
+                        const int q0 = (s - P.n_in - 4) * qps;
+                        const int nqs = (nq - q0) < qps ? (nq - q0) : qps;
+                        off = static_cast<size_t>(FUSED ? P.outf : P.outg) * 4 + static_cast<size_t>(q0) * out_chunk_bytes;
+                        bytes = static_cast<uint32_t>(nqs * out_chunk_bytes);
+                    }
+                    if (dbg & 32) { mbar_arrive(bar(W_FULL + slot)); continue; }  // profiling knob: no weight traffic
+                    mbar_expect_tx(bar(W_FULL + slot), bytes);
+                    const uint32_t dst = smem_u32(ring + slot * kSlotBytes);
+                    for (uint32_t o = 0; o < bytes; o += 18432u) {
+                        const uint32_t n = (bytes - o) < 18432u ? (bytes - o) : 18432u;
+                        bulk_g2s(dst + o, pkb + off + o, n, bar(W_FULL + slot));
                     }
                 }
             }
-            tc_fence_before();
         }
-        __syncthreads();  // all MMAs of this weight stage are complete (mbar) before the next stage overwrites wH/wL
+    } else if (warp == 8) {
+        // =============================== MMA issuer ==================================================================
+        // One lane chosen with elect.sync runs the whole role: the compiler then keeps descriptors, masks and counters in
+        // uniform registers and emits back-to-back UTCHMMA.  (Measured: `if (lane == 0)` or a predicated asm wraps every
+        // MMA in an ELECT loop with R2UR moves, ~200 cycles per k-step; fully unrolled issue code is instruction-fetch
+        // bound, ~380 cycles per k-step.)
+        if (elect_one()) {
+            const uint64_t dAH = make_smem_desc(smem_u32(act), PS, 128);
+            const uint64_t dAL = make_smem_desc(smem_u32(act + 8 * PS), PS, 128);
+            const bool no_mma = (dbg & 1) != 0, no_lo = (dbg & 4) != 0;
+            uint32_t cnt = 0, ph_act0 = 0, ph_act1 = 0;
+            Timeline tl;
+            tl.init(2, blockIdx.x == 0);
+            auto wait_act = [&](int t) {
+                tl.stamp(10 + t);
+                if (t == 0) { mbar_wait(bar(ACT_READY), ph_act0); ph_act0 ^= 1u; }
+                else { mbar_wait(bar(ACT_READY + 1), ph_act1); ph_act1 ^= 1u; }
+                tc_fence_after();
+                tl.stamp(12 + t);
+            };
+            auto commit = [&](int b) {
+                mma_commit(bar(b));
+                tl.stamp(20 + b);
+            };
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                for (int s = 0; s < n_stage; ++s, ++cnt) {
+                    const uint32_t slot = cnt & 1u;
+                    tl.stamp(1);
+                    mbar_wait(bar(W_FULL + slot), (cnt >> 1) & 1u);
+                    tc_fence_after();
+                    tl.stamp(2);
+                    const uint32_t wbase = smem_u32(ring + slot * kSlotBytes);
+                    if (s < P.n_in + 4) {
+                        // ---- 3x3 layer ----
+                        const int nj = (s == P.n_in - 1) ? P.nj_last : 4;
+                        const int Ge = G < nj ? G : nj;
+                        const uint64_t dB = make_smem_desc(wbase, 1024, 128);
+                        int kc = 0, rr = 0;  // k-steps issued into this tile's accumulators; round-robin group
+                        // one k-step = 8 input channels of one tap: [main | comp] += a_hi * [w_hi | w_lo]; comp += a_lo * w_hi
+                        auto kstep = [&](uint32_t tbase, uint64_t a_hi, uint64_t a_lo, uint64_t b, const uint4& m) {
+                            const uint32_t d = tbase + static_cast<uint32_t>(rr * 64);
+                            if (!no_mma) {
+                                mma_tf32(d, a_hi, b, idesc_n(64), kc >= Ge ? 1u : 0u, m.x, m.y, m.z, m.w);
+                                if (!no_lo) mma_tf32(d + 32, a_lo, b, idesc_n(32), 1u, m.x, m.y, m.z, m.w);
+                            }
+                            ++kc;
+                            rr = (rr + 1 == Ge) ? 0 : rr + 1;
+                        };
+                        // taps order[i_lo .. i_hi) of tile t
+                        auto issue = [&](int t, uint64_t order, int i_lo, int i_hi) {
+                            if (nj == 4) {
+                                // tabulated operands: 5 shared-memory loads feed 8 MMAs
+                                const uint32_t a_hi32 = (128u >> 4) | (1u << 14);
+                                const uint32_t b_hi32 = (128u >> 4) | (1u << 14);
+                                const uint32_t b_lo32 = ((wbase >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);
+                                const uint4* pt = prog + (t * 9 + i_lo) * 5;
+#pragma unroll 1
+                                for (int i = i_lo; i < i_hi; ++i, pt += 5) {
+                                    const uint4 m = pt[0];
+                                    const uint4 e[4] = {pt[1], pt[2], pt[3], pt[4]};
+                                    if (!no_mma) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const uint64_t b = (static_cast<uint64_t>(b_hi32) << 32) | (b_lo32 + e[j].z);
+                                            const uint32_t d = tmem + (e[j].w & 0xFFFFu);
+                                            mma_tf32(d, (static_cast<uint64_t>(a_hi32) << 32) | e[j].x, b, idesc_n(64), e[j].w >> 31, m.x, m.y, m.z, m.w);
+                                            if (!no_lo)
+                                                mma_tf32(d + 32, (static_cast<uint64_t>(a_hi32) << 32) | e[j].y, b, idesc_n(32), 1u, m.x, m.y, m.z, m.w);
+                                        }
+                                    }
+                                }
+                                return;
+                            }
+                            const uint32_t tbase = tmem + static_cast<uint32_t>(t * kTileCols);
+#pragma unroll 1
+                            for (int i = i_lo; i < i_hi; ++i) {
+                                const int tap = static_cast<int>((order >> (4 * i)) & 15u);
+                                const int ty = (tap * 11) >> 5, dy = ty - 1, dx = tap - 3 * ty - 1;
+                                const uint4 m = mask_tab[t * 9 + tap];
+                                const uint32_t a_off = static_cast<uint32_t>(GUARD + t * 128 + dy * W + dx);
+                                const uint64_t a_hi = dAH + a_off, a_lo = dAL + a_off, b = dB + static_cast<uint32_t>(tap * nj * 128);
+#pragma unroll 1
+                                for (int j = 0; j < nj; ++j) kstep(tbase, a_hi + 2 * j * PB, a_lo + 2 * j * PB, b + j * 128, m);
+                            }
+                        };
+                        wait_act(0);
+                        if (LINKED) {
+                            issue(0, kOrder0, 0, 6);
+                            wait_act(1);
+                            issue(0, kOrder0, 6, 9);
+                            commit(ACC_DONE);
+                            kc = 0; rr = 0;
+                            issue(1, kOrder1, 0, 4);
+                            commit(WAR0);  // tile 0's rows are no longer read: its epilogue may overwrite them
+                            issue(1, kOrder1, 4, 9);
+                            commit(ACC_DONE + 1);
+                        } else {
+                            issue(0, kOrder0, 0, 9);
+                            commit(ACC_DONE);
+                        }
+                    } else {
+                        // ---- 1x1 output layer, chunks of NW columns: [main NW | comp NW] ----
+                        const int q0 = (s - P.n_in - 4) * qps;
+                        const int nqs = (nq - q0) < qps ? (nq - q0) : qps;
+                        const uint32_t i_main = idesc_n(static_cast<uint32_t>(2 * NW)), i_comp = idesc_n(static_cast<uint32_t>(NW));
+#pragma unroll 1
+                        for (int qi = 0; qi < nqs; ++qi) {
+                            const uint64_t dB = make_smem_desc(wbase + static_cast<uint32_t>(qi * out_chunk_bytes),
+                                                               static_cast<uint32_t>(2 * NW * 16), 128);
+#pragma unroll 1
+                            for (int t = 0; t < T; ++t) {
+                                wait_act(t);
+                                const uint32_t d = tmem + static_cast<uint32_t>(t * kTileCols);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128);
+                                    const uint32_t b_off = static_cast<uint32_t>(j * 4 * NW);  // 2 blocks of 2NW rows x 16 B
+                                    if (!no_mma) {
+                                        mma_tf32(d, dAH + a_off, dB + b_off, i_main, j > 0 ? 1u : 0u, 0u, 0u, 0u, 0u);
+                                        if (!no_lo) mma_tf32(d + NW, dAL + a_off, dB + b_off, i_comp, 1u, 0u, 0u, 0u, 0u);
+                                    }
+                                }
+                                commit(ACC_DONE + t);
+                            }
+                        }
+                    }
+                    commit(W_EMPTY + slot);
+                }
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================================================
+        const int q4 = warp & 3, grp = warp >> 2;
+        const int tile = LINKED ? grp : 0;
+        const int ch0 = LINKED ? 0 : grp * NCH;          // first of this thread's NCH channels
+        const int row = q4 * 32 + lane;                  // TMEM lane = position inside the tile
+        const int pos = tile * 128 + row;                // position inside the unit
+        const int pix = LINKED ? pos : row % HW;
+        const int yy = pix / W, xx = pix % W;
+        const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(tile * kTileCols);
+        const uint32_t b_acc = bar(ACC_DONE + tile), b_act = bar(ACT_READY + tile);
+        unsigned char* my_act = act + (GUARD + pos) * 16;
+        uint32_t ph_acc = 0, ph_war = 0;
+        Timeline tl;
+        tl.init(grp, blockIdx.x == 0 && (tid & 127) == 0);
+
+        auto wait_acc = [&]() {
+            tl.stamp(30);
+            mbar_wait(b_acc, ph_acc);
+            ph_acc ^= 1u;
+            tc_fence_after();
+            tl.stamp(31);
+        };
+        auto wait_war = [&]() {
+            if (LINKED && grp == 0) {
+                tl.stamp(32);
+                mbar_wait(bar(WAR0), ph_war);
+                ph_war ^= 1u;
+                tl.stamp(33);
+            }
+        };
+        auto signal_act = [&]() {
+            tl.stamp(34);
+            fence_proxy_async();  // generic-proxy st.shared -> visible to the tensor core's async-proxy reads
+            tc_fence_before();
+            mbar_arrive(b_act);
+            tl.stamp(35);
+        };
+        // v[c] = sum over the Ge accumulator groups of (main + compensation) for channels ch0 .. ch0+NCH-1
+        auto load_acc = [&](int Ge, float (&v)[NCH]) {
+            if (dbg & 2) {  // profiling knob: no TMEM reads
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) v[i] = 0.f;
+                return;
+            }
+#pragma unroll 1
+            for (int gi = 0; gi < Ge; ++gi) {
+                float m[NCH];
+                tmem_ld<NCH>(t_lane + static_cast<uint32_t>(gi * 64 + ch0), m);
+                if (gi == 0) {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) v[i] = m[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) v[i] += m[i];
+                }
+                tmem_ld<NCH>(t_lane + static_cast<uint32_t>(gi * 64 + 32 + ch0), m);
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) v[i] += m[i];
+            }
+            tl.stamp(36);
+        };
+        // a[NCH] (activated) -> hi / lo planes of this thread's position
+        auto store_act = [&](const float (&a)[NCH]) {
+            if (dbg & 16) return;  // profiling knob: no activation stores
+#pragma unroll
+            for (int c4 = 0; c4 < NCH / 4; ++c4) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_tf32(a[c4 * 4 + q], hi[q], lo[q]);
+                const int plane = ch0 / 4 + c4;
+                st4(reinterpret_cast<float*>(my_act + plane * PS), make_float4(hi[0], hi[1], hi[2], hi[3]));
+                st4(reinterpret_cast<float*>(my_act + (8 + plane) * PS), make_float4(lo[0], lo[1], lo[2], lo[3]));
+            }
+        };
+
+        const float* c_b0 = cst;
+        auto c_blk = [&](int blk, int k) { return cst + 32 + blk * 128 + k * 32; };
+        const float* c_sO = cst + 288;
+        const float* c_tO = cst + 320;
+        const float* c_ob = cst + 352;
+        float sa = 0.f, sb = 0.f;
+        if (FUSED) { sa = __ldg(p_sa); sb = __ldg(p_sb); }
+
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            tl.stamp(40);
+            const int b = LINKED ? unit : unit * SPU + row / HW;
+            const bool valid = b < B;
+            const float* zb = zsrc + static_cast<size_t>(b) * (MODE < 0 ? static_cast<size_t>(Cin) * HW : static_cast<size_t>(g.D));
+            float xres[NCH];
+
+            // ---- in conv: Cin -> 32 in passes of <= 32 input channels; the partial sums meet in registers ------------
+#pragma unroll 1
+            for (int c = 0; c < P.n_in; ++c) {
+                const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
+                const int n4 = ((CI + 7) & ~7) / 4;
+                for (int c4 = (CS == 2 ? grp : 0); c4 < n4; c4 += CS) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ci = c4 * 4 + q;
+                        float v = 0.f;
+                        if (valid && ci < CI) {
+                            const int cg = c * kF + ci;
+                            if (MODE < 0) v = __ldg(zb + cg * HW + pix);
+                            else v = __ldg(zb + half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, cg, 1, yy, xx));
+                        }
+                        split_tf32(v, hi[q], lo[q]);
+                    }
+                    st4(reinterpret_cast<float*>(my_act + c4 * PS), make_float4(hi[0], hi[1], hi[2], hi[3]));
+                    st4(reinterpret_cast<float*>(my_act + (8 + c4) * PS), make_float4(lo[0], lo[1], lo[2], lo[3]));
+                }
+                signal_act();
+                wait_acc();
+                const int nj = (c == P.n_in - 1) ? P.nj_last : 4;
+                float v[NCH];
+                load_acc(G < nj ? G : nj, v);
+                if (c == 0) {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) xres[i] = v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) xres[i] += v[i];
+                }
+                wait_war();
+            }
+            {
+                float a[NCH];
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    xres[i] += c_b0[ch0 + i];
+                    a[i] = fmaxf(fmaf(xres[i], c_blk(0, 0)[ch0 + i], c_blk(0, 1)[ch0 + i]), 0.f);
+                }
+                store_act(a);
+                signal_act();
+            }
+            // ---- two residual blocks ---------------------------------------------------------------------------------
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                float v[NCH], a[NCH];
+                wait_acc();
+                load_acc(G < 4 ? G : 4, v);  // conv1 (second BatchNorm of the block folded into weights and bias)
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) a[i] = fmaxf(v[i] + c_blk(blk, 2)[ch0 + i], 0.f);
+                wait_war();
+                store_act(a);
+                signal_act();
+                wait_acc();
+                load_acc(G < 4 ? G : 4, v);  // conv2 + skip
+                const float* sN = blk == 0 ? c_blk(1, 0) : c_sO;  // the BatchNorm that consumes the updated stream
+                const float* tN = blk == 0 ? c_blk(1, 1) : c_tO;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    xres[i] += v[i] + c_blk(blk, 3)[ch0 + i];
+                    a[i] = fmaxf(fmaf(xres[i], sN[ch0 + i], tN[ch0 + i]), 0.f);
+                }
+                wait_war();
+                store_act(a);
+                signal_act();
+            }
+            // ---- output layer ----------------------------------------------------------------------------------------
+            tl.stamp(41);
+            float ssum = 0.f;
+#pragma unroll 1
+            for (int q = 0; q < nq; ++q) {
+                wait_acc();
+                const float* ob = c_ob + q * NW;
+                if (FUSED) {
+                    // columns [0, PC) = t, [PC, 2PC) = s_raw of channels q*PC ...; AffineCoupling._transform in place on z0
+                    const int PC = NW / 2, m0 = q * PC;
+                    const int i0 = (CS == 2) ? grp * (PC / 2) : 0, i1 = i0 + PC / CS;
+                    float* zo = zdst + static_cast<size_t>(b) * g.D;
+                    for (int i = i0; i < i1; i += 4) {
+                        float tm[4], sm[4], tcp[4], scp[4];
+                        tmem_ld<4>(t_lane + static_cast<uint32_t>(i), tm);
+                        tmem_ld<4>(t_lane + static_cast<uint32_t>(PC + i), sm);
+                        tmem_ld<4>(t_lane + static_cast<uint32_t>(NW + i), tcp);
+                        tmem_ld<4>(t_lane + static_cast<uint32_t>(NW + PC + i), scp);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int m = m0 + i + r;
+                            if (valid && m < g.c0) {
+                                const float t = (tm[r] + tcp[r]) + ob[i + r];
+                                const float sraw = (sm[r] + scp[r]) + ob[PC + i + r];
+                                const int off = half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx);
+                                // coupling.py:107-109: two rounded ops each, no FMA contraction (as in coupling_affine.cu)
+                                const float s = __fadd_rn(__fmul_rn(tanhf(sraw), sa), sb);
+                                zo[off] = __fadd_rn(__fmul_rn(zo[off], expf(s)), t);
+                                ssum += s;
+                            }
+                        }
+                    }
+                } else {
+                    const int i0 = (CS == 2) ? grp * (NW / 2) : 0, i1 = i0 + NW / CS;
+                    for (int i = i0; i < i1; i += 8) {
+                        float mv[8], cv[8];
+                        tmem_ld<8>(t_lane + static_cast<uint32_t>(i), mv);
+                        tmem_ld<8>(t_lane + static_cast<uint32_t>(NW + i), cv);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const int oc = q * NW + i + r;
+                            if (valid && oc < Cout)
+                                zdst[(static_cast<size_t>(b) * Cout + oc) * HW + pix] = (mv[r] + cv[r]) + ob[i + r];
+                        }
+                    }
+                }
+                if (q + 1 < nq) {  // accumulator columns are free for the next chunk
+                    tc_fence_before();
+                    mbar_arrive(b_act);
+                }
+            }
+            if (FUSED) {
+                // per-sample log-det: fixed-order reduction (segmented shuffle -> shared memory -> one thread per sample)
+                constexpr int SEG = HW < 32 ? HW : 32;
+#pragma unroll
+                for (int o = SEG / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                if ((lane & (SEG - 1)) == 0) red[warp * 2 + lane / SEG] = ssum;
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (tid < SPU) {
+                    const int bb = unit * SPU + tid;
+                    if (bb < B) {
+                        float tot = 0.f;
+                        if (HW == 16) tot = red[(tid >> 1) * 2 + (tid & 1)] + red[((tid >> 1) + 4) * 2 + (tid & 1)];
+                        else if (HW == 64) tot = (red[(2 * tid) * 2] + red[(2 * tid + 1) * 2]) + (red[(2 * tid + 4) * 2] + red[(2 * tid + 5) * 2]);
+                        else {
+#pragma unroll
+                            for (int w8 = 0; w8 < 8; ++w8) tot += red[w8 * 2];
+                        }
+                        ldj[bb] = __fadd_rn(ldj[bb], tot);  // coupling.py:110
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            }
+        }
+        tl.stamp(42);
+        tc_fence_before();
     }
 
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(static_cast<uint32_t>(GM::TMEM_COLS)));
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
 }
 
-// ---- packing of the tensor-core section from the FFMA section -------------------------------------------------------
+// =====================================================================================================================
+// packing of the tensor-core section from the FFMA section (once per weight update)
+// =====================================================================================================================
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ pk, float* __restrict__ tc, int Cin, int Cout) {
     const PackLayout L = pack_layout(Cin, Cout, 9);
-    const TcLayout T = tc_layout(Cin, Cout);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < T.total; idx += gridDim.x * blockDim.x) {
-        float val;
-        bool lo = false;
-        if (idx < T.stage0) {
-            const int k = idx - T.consts;
-            const int c = k & 31;
+    const TcPlan P = tc_plan(Cin, Cout);
+    const int c0 = Cout / 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total; idx += gridDim.x * blockDim.x) {
+        float val = 0.f;
+        bool split = true, lo = false;
+        if (idx < P.obias_g) {
+            // constants: b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO
+            const int k = idx - P.consts, c = k & 31;
             if (k < 32) val = pk[L.b0 + c];
             else if (k < 288) {
                 const int blk = (k - 32) / 128, which = ((k - 32) % 128) / 32;
@@ -365,78 +792,127 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
                       : which == 2 ? pk[L.b1[blk] + c] : pk[L.b2[blk] + c];
             } else if (k < 320) val = pk[L.bnO + c];
             else if (k < 352) val = pk[L.bnO + kF + c];
-            else val = pk[L.bout + (k - 352)];
-            tc[idx] = val;
-            continue;
-        }
-        if (idx < T.out_hi) {
-            const int e0 = idx - T.stage0;
-            const int s = e0 / (2 * kTcStage);
-            int r = e0 - s * 2 * kTcStage;
-            lo = r >= kTcStage;
-            if (lo) r -= kTcStage;
-            const int tap = r / 1024, r2 = r - tap * 1024;
-            const int c4 = r2 / 128, n = (r2 % 128) / 4, q = r2 % 4;
-            const int ci = 4 * c4 + q;
-            if (s < T.n_in) {
-                const int cig = s * kF + ci;
-                val = cig < Cin ? pk[L.w0 + (cig * 9 + tap) * kF + n] : 0.f;
+            split = false;
+        } else if (idx < P.in0) {
+            // output bias by column: generic order, then fused order
+            const bool fused = idx >= P.obias_f;
+            const int k = idx - (fused ? P.obias_f : P.obias_g);
+            const int NW = fused ? P.NWf : P.NWg;
+            const int oc = tc_out_channel(fused, k / NW, k % NW, NW, c0, Cout);
+            val = oc >= 0 ? pk[L.bout + oc] : 0.f;
+            split = false;
+        } else if (idx < P.outg) {
+            // 3x3 stages: [tap][j][k4][n (64: w_hi | w_lo)][4 ci]
+            int e = idx - P.in0, cig_base, base, nj;
+            if (idx < P.mid0) {
+                const int pass = e / (kSlotBytes / 4);
+                e -= pass * (kSlotBytes / 4);
+                nj = (pass == P.n_in - 1) ? P.nj_last : 4;
+                cig_base = pass * kF;
+                base = -1;
             } else {
-                const int i = s - T.n_in;
-                const int base = (i & 1) ? L.w2[i >> 1] : L.w1[i >> 1];
-                val = pk[base + (ci * 9 + tap) * kF + n];
+                e = idx - P.mid0;
+                const int i = e / (kSlotBytes / 4);
+                e -= i * (kSlotBytes / 4);
+                nj = 4;
+                cig_base = 0;
+                base = (i & 1) ? L.w2[i >> 1] : L.w1[i >> 1];
             }
+            const int ks = e / 512, r = e % 512;           // k-step (tap*nj + j), 512 floats each
+            const int tap = ks / nj, j = ks % nj;
+            const int k4 = r / 256, n = (r % 256) / 4, q = r % 4;
+            const int ci = cig_base + 8 * j + 4 * k4 + q, co = n & 31;
+            lo = n >= 32;
+            if (base < 0) val = ci < Cin ? pk[L.w0 + (ci * 9 + tap) * kF + co] : 0.f;
+            else val = pk[base + (ci * 9 + tap) * kF + co];
         } else {
-            int e0 = idx - T.out_hi;
-            lo = e0 >= T.n_chunks * 1024;
-            if (lo) e0 -= T.n_chunks * 1024;
-            const int chunk = e0 / 1024, r2 = e0 - chunk * 1024;
-            const int c4 = r2 / 128, n = (r2 % 128) / 4, q = r2 % 4;
-            const int ci = 4 * c4 + q;
-            val = pk[L.wout + (chunk * kF + ci) * kF + n];  // pack_wn layout: ((o>>5)*J + j)*32 + (o&31), J = 32
+            // output chunks: [j][k4][n (2NW: hi | lo)][4 ci]
+            const bool fused = idx >= P.outf;
+            const int NW = fused ? P.NWf : P.NWg;
+            const int e = idx - (fused ? P.outf : P.outg);
+            const int q_chunk = e / (64 * NW), r = e % (64 * NW);
+            const int blkk = r / (8 * NW), r2 = r % (8 * NW);  // block (j*2 + k4) of 2NW rows x 4 floats
+            const int n = r2 / 4, q = r2 % 4;
+            const int ci = 4 * blkk + q;
+            lo = n >= NW;
+            const int oc = tc_out_channel(fused, q_chunk, lo ? n - NW : n, NW, c0, Cout);
+            val = oc >= 0 ? pk[L.wout + ((oc >> 5) * kF + ci) * kF + (oc & 31)] : 0.f;  // pack_wn layout, J = 32
         }
-        const float hi = __uint_as_float(__float_as_uint(val) & 0xFFFFE000u);
-        tc[idx] = lo ? val - hi : hi;
+        if (split) {
+            float hi, l;
+            split_tf32(val, hi, l);
+            val = lo ? l : hi;
+        }
+        tc[idx] = val;
     }
 }
 
 int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st) {
-    const TcLayout T = tc_layout(Cin, Cout);
-    int blocks = (T.total + 255) / 256;
+    const TcPlan P = tc_plan(Cin, Cout);
+    int blocks = (P.total + 255) / 256;
     if (blocks > kSMs * 8) blocks = kSMs * 8;
     pack_tc_kernel<<<blocks, 256, 0, st>>>(pk_ffma, pk_tc_section, Cin, Cout);
     return launch_status();
 }
 
-template <int H, int W, int S, int MODE>
-static int launch_tc(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
-                     cudaStream_t st) {
-    using GM = TcGeom<H, W, S>;
-    auto kern = convnet_tc_kernel<H, W, S, MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(GM::SMEM));
-        attr_set = true;
-    }
-    kern<<<(B + S - 1) / S, 128, GM::SMEM, st>>>(zsrc, out, pk_tc, g, Cin, Cout, B, g_tune[4]);
+// =====================================================================================================================
+// launch
+// =====================================================================================================================
+template <int H, int W, int MODE, bool FUSED>
+static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
+                     const float* sa, const float* sb, int G, cudaStream_t st) {
+    using GM = TcGeom<H, W>;
+    const int dbg = g_tune[4];
+    const TcPlan P = tc_plan(Cin, Cout);
+    const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
+    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16;
+    if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
+    auto kern = convnet_tc_kernel<H, W, MODE, FUSED>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const int n_units = (B + GM::SPU - 1) / GM::SPU;
+    const int grid = n_units < kSMs ? n_units : kSMs;
+    kern<<<grid, kThreads, smem, st>>>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, dbg);
     return launch_status();
 }
 
-template <int MODE>
-static int tc_by_size(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B, int h,
-                      int w, cudaStream_t st) {
-    if (Cout > 768) return NFB_ERR_UNSUPPORTED;  // constants buffer
-    if (h == 16 && w == 16) return launch_tc<16, 16, 1, MODE>(zsrc, out, pk_tc, g, Cin, Cout, B, st);
-    if (h == 8 && w == 8) return launch_tc<8, 8, 2, MODE>(zsrc, out, pk_tc, g, Cin, Cout, B, st);
-    if (h == 4 && w == 4) return launch_tc<4, 4, 3, MODE>(zsrc, out, pk_tc, g, Cin, Cout, B, st);
+template <int MODE, bool FUSED>
+static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
+                      int h, int w, const float* sa, const float* sb, int G, cudaStream_t st) {
+    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
+    if (h == 8 && w == 8) return launch_tc<8, 8, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
+    if (h == 4 && w == 4) return launch_tc<4, 4, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
     return NFB_ERR_UNSUPPORTED;
+}
+
+static int tc_groups() {
+    const int G = g_tune[5];  // accumulator groups per layer (developer knob); 0 = default
+    return G >= 1 && G <= 4 ? G : 3;
 }
 
 int convnet_tc_dispatch(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
                         int B, int h, int w, cudaStream_t st) {
-    if (mode == NFB_SPLIT_CHECKER) return tc_by_size<NFB_SPLIT_CHECKER>(zsrc, out, pk_tc, g, Cin, Cout, B, h, w, st);
-    if (mode == NFB_SPLIT_CHANNEL) return tc_by_size<NFB_SPLIT_CHANNEL>(zsrc, out, pk_tc, g, Cin, Cout, B, h, w, st);
-    return tc_by_size<-1>(zsrc, out, pk_tc, g, Cin, Cout, B, h, w, st);
+    const int G = tc_groups();
+    if (mode == NFB_SPLIT_CHECKER)
+        return tc_by_size<NFB_SPLIT_CHECKER, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
+    if (mode == NFB_SPLIT_CHANNEL)
+        return tc_by_size<NFB_SPLIT_CHANNEL, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
+    return tc_by_size<-1, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
+}
+
+int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout, int B,
+                               const float* sa, const float* sb, cudaStream_t st) {
+    const int G = tc_groups();
+    if (Cout != 2 * g.c0) return NFB_ERR_SHAPE;
+    if (mode == NFB_SPLIT_CHECKER)
+        return tc_by_size<NFB_SPLIT_CHECKER, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, G, st);
+    if (mode == NFB_SPLIT_CHANNEL)
+        return tc_by_size<NFB_SPLIT_CHANNEL, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, G, st);
+    return NFB_ERR_UNSUPPORTED;
 }
 
 }  // namespace nfb
+
+// developer entry point (not part of include/nfb200.h): device buffer of 3 * 512 uint64 for CTA 0's timeline, or NULL
+extern "C" int nfb_debug_timeline(unsigned long long* buf) {
+    return static_cast<int>(cudaMemcpyToSymbol(nfb::g_tl_buf, &buf, sizeof(buf)));
+}

@@ -104,8 +104,35 @@ class AffineCoupling(AbstractCoupling):
         in_chs, self.out_chs = self._half_channels()
         self.net = MLP(in_chs, self.out_chs * 2) if len(dims) == 1 else ConvNet(in_chs, self.out_chs * 2)
 
+    # conditioner + bijection + log-det as ONE tensor-core kernel (nfb_convnet_affine_fwd); False = two kernels
+    fused_conditioner = True
+
+    def forward_fused(self, z, ldj, inplace=False):
+        """ConvNet conditioner and the affine transform as one kernel; (t, s) never leave the SM.  The kernel works in
+        place on z: `inplace=False` (the layer API) first copies z so that the caller's tensor is left alone, like the
+        reference's merged output; `Compose` passes inplace=True for a z it owns.  None: shape / mode not covered."""
+        if (not self.fused_conditioner or z.dim() != 4 or self.net.training or type(self.net) is not ConvNet
+                or self._recording(z, ldj)):
+            return None
+        B, C, H, W = z.shape
+        h, w = (H // 2, W // 2) if self.mode == L.SPLIT_CHECKER else (H, W)
+        if (h, w) not in ((16, 16), (8, 8), (4, 4)) or B == 0:
+            return None
+        out = z if inplace else z.clone()
+        rc = L.lib().nfb_convnet_affine_fwd(L.ptr(out), L.ptr(ldj), L.ptr(self.net.packed()),
+                                            L.ptr(self.s_log_scale.data), L.ptr(self.s_bias.data), B, C, H, W, self.mode,
+                                            int(self.odd), L.stream())
+        if rc == L.ERR_UNSUPPORTED:
+            return None
+        L.check(rc)
+        return out, ldj
+
     def _run(self, z, ldj, inverse):
         B, C, H, W = self._geom(z)
+        if not inverse:
+            out = self.forward_fused(z, ldj)
+            if out is not None:
+                return out
         params = self._params(z)
         if not inverse and self._recording(z, ldj):
             return G.AffineCouplingFn.apply(z, params, ldj, self.s_log_scale, self.s_bias, self.mode, self.odd)

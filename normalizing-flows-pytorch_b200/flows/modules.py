@@ -269,6 +269,7 @@ class Compose(nn.Module):
         # the fused peepholes are inference kernels; with autograd recording every layer runs through its own Function
         fuse = self.fuse_steps if not (torch.is_grad_enabled() and (z.requires_grad or log_df_dz.requires_grad or any(
             p.requires_grad for p in self.parameters()))) else 0
+        owned = False  # z is a tensor produced inside this loop (safe to update in place)
         while i < n:
             layer = layers[i]
             # peepholes (same arithmetic, fewer launches): a whole Glow step ActNorm -> 1x1 conv -> AffineCoupling as one
@@ -285,8 +286,17 @@ class Compose(nn.Module):
                 if out is not None:
                     z, log_df_dz = out
                     i += 2
+                    owned = True
+                    continue
+            # an affine coupling whose input this loop produced itself: conditioner + transform in place, one kernel
+            if fuse and owned and hasattr(layer, 'forward_fused'):
+                out = layer.forward_fused(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), inplace=True)
+                if out is not None:
+                    z, log_df_dz = out
+                    i += 1
                     continue
             z, log_df_dz = layer(z, log_df_dz)
+            owned = True  # every layer returns a fresh z (the reference's layers never alias their input either)
             i += 1
         return z, log_df_dz
 
