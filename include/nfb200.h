@@ -190,9 +190,6 @@ int nfb_weight_norm(const float* v, const float* g, float* w_out, int O, int Ikk
  * mid_block.1.net.5, out_block.2, then (weight, bias, running_mean, running_var) of mid_block.0.net.0,
  * mid_block.0.net.3, mid_block.1.net.0, mid_block.1.net.3, out_block.0.  conv != 0: ConvNet (3x3 / 1x1), else MLP. */
 int nfb_resnet_pack_size(int in_ch, int out_ch, int conv);
-/* developer knob: select a kernel variant (key 0/1/2: FFMA ConvNet tile shape at 16x16 / 8x8 / 4x4; key 3: 0 = tensor-core
- * conditioner (default), 2 = FP32-FFMA conditioner; key 5: accumulator groups of the tensor-core kernel; value 0 = default). */
-int nfb_set_tuning(int key, int value);
 int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int out_ch, int conv, float wn_eps,
                     float bn_eps, nfb_stream_t stream);
 /* params_out (B, out_ch, h, w) = ConvNet(z1).  mode = NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL: `src` is the coupling's
@@ -201,24 +198,29 @@ int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int o
  * conditioner input: 32x32 (one 2-CTA cluster per sample), 16x16, 8x8, 4x4 (else NFB_ERR_UNSUPPORTED). */
 int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
                     int odd, int in_ch, int out_ch, nfb_stream_t stream);
+/* Same with an explicit kernel selection (the library keeps no mutable state).  flags = 0 is nfb_convnet_fwd: the
+ * tensor-core kernel (tcgen05, error-compensated TF32) where it applies (16x16 / 8x8 / 4x4), else the FP32-FFMA kernels.
+ *   NFB_CONV_FFMA            use the FP32-FFMA kernels
+ *   NFB_CONV_VARIANT_MASK    thread-tile variant of the FP32-FFMA kernel for this spatial size (0 = default)
+ *   NFB_CONV_GROUPS(g)       accumulator groups per layer of the tensor-core kernel, 1..4 (0 = default 3)
+ *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results */
+#define NFB_CONV_VARIANT_MASK 0x7
+#define NFB_CONV_FFMA 0x8
+#define NFB_CONV_GROUPS_SHIFT 4
+#define NFB_CONV_GROUPS(g) ((g) << NFB_CONV_GROUPS_SHIFT)
+#define NFB_CONV_DEBUG_SHIFT 8
+#define NFB_CONV_DEBUG(bits) ((bits) << NFB_CONV_DEBUG_SHIFT)
+int nfb_convnet_fwd_ex(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
+                       int odd, int in_ch, int out_ch, int flags, nfb_stream_t stream);
 /* AffineCoupling.forward with its ConvNet conditioner as ONE kernel, in place on z (coupling.py:32-36,104-112 +
  * modules.py:416-438): z1 = pass-through half of z is gathered by the kernel, params = ConvNet(z1) is computed on the
  * tensor cores (tcgen05, error-compensated TF32) and consumed from tensor memory -- it never reaches shared or global
  * memory -- z0 <- z0*exp(tanh(s_raw)*a + b) + t is written over z0 inside z, ldj[b] += sum(s).  z1 stays untouched, so
  * the result equals the reference's merged output.  `packed` from nfb_resnet_pack(in_ch = c0, out_ch = 2*c0).
- * Conditioner input sizes 16x16 / 8x8 / 4x4; otherwise NFB_ERR_UNSUPPORTED (run nfb_convnet_fwd + nfb_affine_coupling_fwd). */
+ * Conditioner input sizes 16x16 / 8x8 / 4x4; otherwise (or with NFB_CONV_FFMA in flags) NFB_ERR_UNSUPPORTED: run
+ * nfb_convnet_fwd + nfb_affine_coupling_fwd.  flags as for nfb_convnet_fwd_ex. */
 int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale, const float* s_bias,
-                           int B, int C, int H, int W, int mode, int odd, nfb_stream_t stream);
-/* One whole Glow flow step (glow.py:27-29) in ONE launch: ActNorm.forward (modules.py:246-250) ->
- * InvertibleConv1x1.forward (modules.py:470-482, Wm = the matrix from nfb_invconv1x1_weight) -> AffineCoupling.forward
- * (coupling.py:32-36,104-112) with its ConvNet conditioner (packed by nfb_resnet_pack).  The conditioner output never
- * leaves shared memory.  z_out must not alias z_in.  NFB_ERR_UNSUPPORTED for conditioner sizes other than 16x16 / 8x8 /
- * 4x4 or when one sample plus the C x C matrix exceeds the staging buffer: run the three layers separately. */
-int nfb_glow_step_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* an_log_scale,
-                      const float* an_bias, const float* Wm, const float* log_s, const float* packed,
-                      const float* s_log_scale, const float* s_bias, int B, int C, int H, int W, int mode, int odd,
-                      nfb_stream_t stream);
-
+                           int B, int C, int H, int W, int mode, int odd, int flags, nfb_stream_t stream);
 /* Flow++ conditioner (coupling.py:160-167: Conv2d(in,32,3) -> GatedConv2d -> LayerNorm -> GatedAttn(4 heads) ->
  * LayerNorm -> Conv2d(32,out,3); modules.py:519-578) as ONE kernel.  `tensors`: HOST array of 15 device pointers:
  * net.0 weight packed by nfb_pack_conv3x3, net.0.bias, net.1.op weight packed, net.1.op.bias, net.2.weight, net.2.bias,

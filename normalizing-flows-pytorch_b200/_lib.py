@@ -14,6 +14,21 @@ LIB_PATH = os.path.join(_HERE, 'libnfb200.so')
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'nfb200.h')
 
 SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
+# kernel selection flags of nfb_convnet_fwd_ex / nfb_convnet_affine_fwd (include/nfb200.h)
+CONV_FFMA = 0x8
+
+
+def conv_variant(v):
+    return v & 0x7
+
+
+def conv_groups(g):
+    return g << 4
+
+
+def conv_debug(bits):
+    return bits << 8
+
 ERR_NULL, ERR_SHAPE, ERR_SPLIT, ERR_UNSUPPORTED = -1, -2, -3, -4
 
 _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
@@ -50,11 +65,10 @@ _SIGNATURES = {
     'nfb_gauss_nll': [_P, _P, _P, _P, _I, _I, _P],
     'nfb_weight_norm': [_P, _P, _P, _I, _I, _F, _P],
     'nfb_resnet_pack_size': [_I, _I, _I],
-    'nfb_set_tuning': [_I, _I],
     'nfb_resnet_pack': [_P, _P, _I, _I, _I, _F, _F, _P],
     'nfb_convnet_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    'nfb_convnet_affine_fwd': [_P] * 5 + [_I] * 6 + [_P],
-    'nfb_glow_step_fwd': [_P] * 11 + [_I] * 6 + [_P],
+    'nfb_convnet_fwd_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_convnet_affine_fwd': [_P] * 5 + [_I] * 7 + [_P],
     'nfb_pack_conv3x3': [_P, _P, _I, _I, _P],
     'nfb_flowpp_cond_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_flowpp_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -75,29 +75,11 @@ __global__ void pack_bn_kernel(const float* __restrict__ w, const float* __restr
 // ---------------------------------------------------------------------------------------------------------
 // fused ConvNet
 // ---------------------------------------------------------------------------------------------------------
-// Arguments of the fused flow step (ActNorm -> InvertibleConv1x1 -> AffineCoupling in one launch).
-struct StepArgs {
-    const float* z_in;      // (B, C, Hf, Wf) input of the step
-    float* z_out;           // output of the step (also the staging area of the 1x1-conv result)
-    const float* ldj_in;
-    float* ldj_out;
-    const float* an_ls;     // ActNorm log_scale / bias (C)
-    const float* an_b;
-    const float* M;         // 1x1 conv matrix W (C x C, row-major) and its log_s (C)
-    const float* log_s;
-    const float* sa;        // AffineCoupling s_log_scale / s_bias (device scalars)
-    const float* sb;
-};
-
 // MODE: NFB_SPLIT_CHECKER / NFB_SPLIT_CHANNEL gather z1 from the coupling's z; MODE < 0: x is the (B,Cin,H,W) input.
-// STEP: whole Glow flow step -- prologue = ActNorm + 1x1 conv (staged through the idle second weight buffer, result
-// written to z_out), epilogue = affine transform of z0 with (t, s) taken from shared memory + per-sample log-det;
-// the conditioner output never reaches HBM.
-template <int H, int W, int NT, int OCT, int MODE, bool STEP>
+template <int H, int W, int NT, int OCT, int MODE>
 __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restrict__ zsrc, float* __restrict__ out,
                                                           const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
-                                                          int B, StepArgs sa) {
-    __shared__ float red[33];
+                                                          int B) {
     constexpr int PGS = H * W / 4;         // pixel groups per sample
     constexpr int NOG = kF / OCT;          // groups of output channels
     constexpr int NPG = NT / NOG;          // pixel groups per CTA
@@ -156,46 +138,8 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
 
     prefetch_stage(0);
     for (int i = t; i < kF * CHS; i += NT) bufA[i] = 0.f;  // includes the zero halo rows
-    if (STEP) {
-        // ---- prologue: z_out = W @ ((z_in - bias) / exp(log_scale)), ldj += (sum log_s - sum log_scale) * HW -------
-        const int D = g.D, C = g.C, HW = g.HW;
-        float* zst = wbuf + kWStage;           // S*D floats: the normalised input (second weight buffer is idle)
-        float* Mt = zst + S * D;               // C*C, transposed: Mt[ci][co]
-        for (int i = t; i < C * C; i += NT) { const int ci = i / C, co = i - ci * C; Mt[i] = __ldg(sa.M + co * C + ci); }
-        for (int i = t; i < S * D; i += NT) {
-            const int ss = i / D, e = i - ss * D;
-            const int bb = blockIdx.x * S + ss;
-            float v = 0.f;
-            if (bb < B) {
-                const int c = e / HW;
-                v = __fdiv_rn(__fsub_rn(__ldg(sa.z_in + static_cast<size_t>(bb) * D + e), __ldg(sa.an_b + c)),
-                              expf(__ldg(sa.an_ls + c)));  // modules.py:246
-            }
-            zst[i] = v;
-        }
-        if (t < S && blockIdx.x * S + t < B) {
-            const int bb = blockIdx.x * S + t;
-            float an = 0.f, cv = 0.f;
-            for (int c = 0; c < C; ++c) { an -= __ldg(sa.an_ls + c); cv += __ldg(sa.log_s + c); }
-            float l = sa.ldj_in[bb];
-            l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));   // modules.py:249
-            l = __fadd_rn(l, __fmul_rn(cv, static_cast<float>(HW)));   // modules.py:480
-            sa.ldj_out[bb] = l;
-        }
-        __syncthreads();
-        for (int i = t; i < S * D; i += NT) {
-            const int ss = i / D, e = i - ss * D;
-            const int bb = blockIdx.x * S + ss;
-            if (bb >= B) continue;
-            const int co = e / HW, p = e - co * HW;
-            const float* zc = zst + ss * D + p;
-            float acc = 0.f;
-            for (int ci = 0; ci < C; ++ci) acc = fmaf(Mt[ci * C + co], zc[ci * HW], acc);  // modules.py:477
-            sa.z_out[static_cast<size_t>(bb) * D + e] = acc;
-        }
-    }
-    __syncthreads();  // STEP: z_out written by this CTA is visible to all its threads; staging buffer free again
-    const float* src = STEP ? sa.z_out : zsrc;
+    __syncthreads();
+    const float* src = zsrc;
 
     float xres[OCT][4];  // residual stream: this thread's OCT channels x 4 pixels
     float acc[OCT][4];
@@ -218,7 +162,6 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
             if (bb < B) {
                 const int j = (c * kF + ci) * (H * W) + rem;  // index inside the (Cin, H, W) conditioner input
                 if (MODE < 0) v = __ldg(src + static_cast<size_t>(bb) * Cin * (H * W) + j);
-                else if (STEP) v = src[static_cast<size_t>(bb) * g.D + half_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, j, 1)];
                 else v = __ldg(src + static_cast<size_t>(bb) * g.D + half_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, j, 1));
             }
             bufA[ci * CHS + ss * (H + 2) * W + W + rem] = v;  // +W: skip the zero row above
@@ -313,51 +256,21 @@ __global__ void __launch_bounds__(NT) convnet_fused_kernel(const float* __restri
                 if (oc < Cout) {
                     const float bias = __ldg(pk + L.bout + oc);
                     const float4 r = make_float4(acc[o][0] + bias, acc[o][1] + bias, acc[o][2] + bias, acc[o][3] + bias);
-                    if (STEP) st4(wbuf + 1024 + s * g.D + (oc * H + y) * W + x0, r);  // params stay on chip
-                    else st4(out + ((static_cast<size_t>(b) * Cout + oc) * H + y) * W + x0, r);
+                    st4(out + ((static_cast<size_t>(b) * Cout + oc) * H + y) * W + x0, r);
                 }
             }
-        }
-    }
-    if (STEP) {
-        // ---- epilogue: AffineCoupling._transform (coupling.py:104-112) on the transformed half, in place on z_out ----
-        __syncthreads();
-        const float a = __ldg(sa.sa), bsh = __ldg(sa.sb);
-        for (int ss = 0; ss < S; ++ss) {
-            const int bb = blockIdx.x * S + ss;
-            float accs = 0.f;
-            if (bb < B) {
-                const float* sp = wbuf + 1024 + ss * g.D;
-                float* zo = sa.z_out + static_cast<size_t>(bb) * g.D;
-                for (int e = t; e < g.D; e += NT) {
-                    int idx;
-                    if (classify<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, e, idx)) {
-                        const float sv = __fadd_rn(__fmul_rn(tanhf(sp[g.n0 + idx]), a), bsh);
-                        zo[e] = __fadd_rn(__fmul_rn(zo[e], expf(sv)), sp[idx]);
-                        accs += sv;
-                    }
-                }
-            }
-            accs = block_sum(accs, red);
-            if (t == 0 && bb < B) sa.ldj_out[bb] += accs;
         }
     }
 }
 
-template <int H, int W, int NT, int OCT, int MODE, bool STEP = false>
+template <int H, int W, int NT, int OCT, int MODE>
 static int launch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
-                          cudaStream_t st, const StepArgs& sa = StepArgs{}) {
+                          cudaStream_t st) {
     constexpr int S = (NT / (kF / OCT)) / (H * W / 4);
     constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 2 * kWStage) * sizeof(float);
-    // staging (prologue: S samples + the C x C matrix; epilogue: S samples of params after the chunk weights) must fit
-    if (STEP && (S * g.D + g.C * g.C > kWStage || 1024 + S * g.D > kWStage)) return NFB_ERR_UNSUPPORTED;
-    auto kern = convnet_fused_kernel<H, W, NT, OCT, MODE, STEP>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
-    kern<<<(B + S - 1) / S, NT, smem, st>>>(zsrc, out, pk, g, Cin, Cout, B, sa);
+    auto kern = convnet_fused_kernel<H, W, NT, OCT, MODE>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<(B + S - 1) / S, NT, smem, st>>>(zsrc, out, pk, g, Cin, Cout, B);
     return launch_status();
 }
 
@@ -554,33 +467,28 @@ static int launch_cluster32(const float* zsrc, float* out, const float* pk, cons
                             cudaStream_t st) {
     constexpr size_t smem = (static_cast<size_t>(kF) * 18 * 32 + 2 * kWStage) * sizeof(float);
     auto kern = convnet_cluster32_kernel<MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     kern<<<2 * B, 512, smem, st>>>(zsrc, out, pk, g, Cin, Cout, B);
     return launch_status();
 }
 
-int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // runtime variant selection (nfb_set_tuning); 0 = default
-
 template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
-                            int h, int w, cudaStream_t st) {
-    if (g_tune[3] != 2) {  // default: tensor-core (tcgen05 3xTF32) kernel; 2 = FP32-FFMA kernels below (developer knob)
-        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_plan(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, st);
+                            int h, int w, int flags, cudaStream_t st) {
+    if (!(flags & NFB_CONV_FFMA)) {  // default: tensor-core (tcgen05 3xTF32) kernel
+        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_plan(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, flags, st);
         if (rc != NFB_ERR_UNSUPPORTED) return rc;
     }
+    const int variant = flags & NFB_CONV_VARIANT_MASK;
 #define NFB_CONV(H_, W_, NT_, OCT_) return launch_convnet<H_, W_, NT_, OCT_, MODE>(zsrc, out, pk, g, Cin, Cout, B, st)
     if (h == 16 && w == 16) {
-        switch (g_tune[0]) {
+        switch (variant) {
             case 1: NFB_CONV(16, 16, 512, 4);
             default: NFB_CONV(16, 16, 256, 8);
         }
     }
     if (h == 8 && w == 8) {
-        switch (g_tune[1]) {
+        switch (variant) {
             case 1: NFB_CONV(8, 8, 64, 8);
             case 2: NFB_CONV(8, 8, 256, 2);
             case 3: NFB_CONV(8, 8, 256, 4);
@@ -588,7 +496,7 @@ static int dispatch_convnet(const float* zsrc, float* out, const float* pk, cons
         }
     }
     if (h == 4 && w == 4) {
-        switch (g_tune[2]) {
+        switch (variant) {
             case 1: NFB_CONV(4, 4, 32, 8);
             case 2: NFB_CONV(4, 4, 64, 2);
             case 3: NFB_CONV(4, 4, 128, 4);
@@ -686,12 +594,6 @@ __global__ void __launch_bounds__(256) mlp_fused_kernel(const float* __restrict_
 
 using namespace nfb;
 
-extern "C" int nfb_set_tuning(int key, int value) {
-    if (key < 0 || key >= 8) return NFB_ERR_SHAPE;
-    g_tune[key] = value;
-    return NFB_OK;
-}
-
 extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
     if (!conv) return pack_layout(in_ch, out_ch, 1).total;
@@ -737,8 +639,8 @@ extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, 
     return pack_tc_launch(packed, packed + tc_plan(in_ch, out_ch).base, in_ch, out_ch, st);
 }
 
-extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
-                               int mode, int odd, int in_ch, int out_ch, nfb_stream_t stream) {
+extern "C" int nfb_convnet_fwd_ex(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
+                                  int mode, int odd, int in_ch, int out_ch, int flags, nfb_stream_t stream) {
     if (!src || !params_out || !packed) return NFB_ERR_NULL;
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
     cudaStream_t st = as_stream(stream);
@@ -746,53 +648,32 @@ extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float*
     if (mode < 0) {  // src is the (B, in_ch, H, W) conditioner input itself
         if (B <= 0 || H <= 0 || W <= 0) return NFB_ERR_SHAPE;
         g = SplitGeom{};
-        return dispatch_convnet<-1>(src, params_out, packed, g, in_ch, out_ch, B, H, W, st);
+        return dispatch_convnet<-1>(src, params_out, packed, g, in_ch, out_ch, B, H, W, flags, st);
     }
     const int rc = make_geom(g, B, C, H, W, mode, odd);
     if (rc != NFB_OK) return rc;
     if (g.c0 != in_ch) return NFB_ERR_SHAPE;
-    if (mode == NFB_SPLIT_CHECKER) return dispatch_convnet<NFB_SPLIT_CHECKER>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
-    if (mode == NFB_SPLIT_CHANNEL) return dispatch_convnet<NFB_SPLIT_CHANNEL>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, st);
+    if (mode == NFB_SPLIT_CHECKER) return dispatch_convnet<NFB_SPLIT_CHECKER>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, flags, st);
+    if (mode == NFB_SPLIT_CHANNEL) return dispatch_convnet<NFB_SPLIT_CHANNEL>(src, params_out, packed, g, in_ch, out_ch, B, g.h, g.w, flags, st);
     return NFB_ERR_SHAPE;
 }
 
+extern "C" int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
+                               int mode, int odd, int in_ch, int out_ch, nfb_stream_t stream) {
+    return nfb_convnet_fwd_ex(src, params_out, packed, B, C, H, W, mode, odd, in_ch, out_ch, 0, stream);
+}
+
 extern "C" int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale,
-                                      const float* s_bias, int B, int C, int H, int W, int mode, int odd,
+                                      const float* s_bias, int B, int C, int H, int W, int mode, int odd, int flags,
                                       nfb_stream_t stream) {
     if (!z || !ldj || !packed || !s_log_scale || !s_bias) return NFB_ERR_NULL;
     SplitGeom g;
     const int rc = make_geom(g, B, C, H, W, mode, odd);
     if (rc != NFB_OK) return rc;
     if (mode != NFB_SPLIT_CHECKER && mode != NFB_SPLIT_CHANNEL) return NFB_ERR_UNSUPPORTED;
-    if (g_tune[3] == 2) return NFB_ERR_UNSUPPORTED;
+    if (flags & NFB_CONV_FFMA) return NFB_ERR_UNSUPPORTED;
     return convnet_affine_tc_dispatch(z, ldj, packed + tc_plan(g.c0, 2 * g.c0).base, g, mode, g.c0, 2 * g.c0, B, s_log_scale,
-                                      s_bias, as_stream(stream));
-}
-
-template <int MODE>
-static int step_by_size(const SplitGeom& g, const float* pk, int Cin, int Cout, int B, cudaStream_t st, const StepArgs& sa) {
-    if (g.h == 16 && g.w == 16) return launch_convnet<16, 16, 256, 8, MODE, true>(nullptr, nullptr, pk, g, Cin, Cout, B, st, sa);
-    if (g.h == 8 && g.w == 8) return launch_convnet<8, 8, 128, 4, MODE, true>(nullptr, nullptr, pk, g, Cin, Cout, B, st, sa);
-    if (g.h == 4 && g.w == 4) return launch_convnet<4, 4, 128, 2, MODE, true>(nullptr, nullptr, pk, g, Cin, Cout, B, st, sa);
-    return NFB_ERR_UNSUPPORTED;
-}
-
-extern "C" int nfb_glow_step_fwd(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out,
-                                 const float* an_log_scale, const float* an_bias, const float* Wm, const float* log_s,
-                                 const float* packed, const float* s_log_scale, const float* s_bias, int B, int C, int H,
-                                 int W, int mode, int odd, nfb_stream_t stream) {
-    if (!z_in || !z_out || !ldj_in || !ldj_out || !an_log_scale || !an_bias || !Wm || !log_s || !packed || !s_log_scale ||
-        !s_bias)
-        return NFB_ERR_NULL;
-    if (z_in == z_out) return NFB_ERR_UNSUPPORTED;
-    SplitGeom g;
-    const int rc = make_geom(g, B, C, H, W, mode, odd);
-    if (rc != NFB_OK) return rc;
-    const StepArgs sa{z_in, z_out, ldj_in, ldj_out, an_log_scale, an_bias, Wm, log_s, s_log_scale, s_bias};
-    cudaStream_t st = as_stream(stream);
-    if (mode == NFB_SPLIT_CHECKER) return step_by_size<NFB_SPLIT_CHECKER>(g, packed, g.c0, 2 * g.c0, B, st, sa);
-    if (mode == NFB_SPLIT_CHANNEL) return step_by_size<NFB_SPLIT_CHANNEL>(g, packed, g.c0, 2 * g.c0, B, st, sa);
-    return NFB_ERR_UNSUPPORTED;
+                                      s_bias, flags, as_stream(stream));
 }
 
 extern "C" int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd,

@@ -150,11 +150,10 @@ __host__ __device__ inline int tc_out_channel(bool fused, int q, int col, int NW
     return col < PC ? m : c0 + m;
 }
 
-extern int g_tune[8];
 int convnet_tc_dispatch(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
-                        int B, int h, int w, cudaStream_t st);
+                        int B, int h, int w, int flags, cudaStream_t st);
 int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout, int B,
-                               const float* sa, const float* sb, cudaStream_t st);
+                               const float* sa, const float* sb, int flags, cudaStream_t st);
 int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace nfb

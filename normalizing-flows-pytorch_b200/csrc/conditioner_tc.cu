@@ -860,9 +860,11 @@ int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout
 // =====================================================================================================================
 template <int H, int W, int MODE, bool FUSED>
 static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
-                     const float* sa, const float* sb, int G, cudaStream_t st) {
+                     const float* sa, const float* sb, int flags, cudaStream_t st) {
     using GM = TcGeom<H, W>;
-    const int dbg = g_tune[4];
+    const int dbg = (flags >> NFB_CONV_DEBUG_SHIFT) & 0xff;
+    const int gq = (flags >> NFB_CONV_GROUPS_SHIFT) & 7;
+    const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer
     const TcPlan P = tc_plan(Cin, Cout);
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16;
@@ -877,36 +879,29 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk
 
 template <int MODE, bool FUSED>
 static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
-                      int h, int w, const float* sa, const float* sb, int G, cudaStream_t st) {
-    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
-    if (h == 8 && w == 8) return launch_tc<8, 8, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
-    if (h == 4 && w == 4) return launch_tc<4, 4, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, st);
+                      int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
+    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    if (h == 8 && w == 8) return launch_tc<8, 8, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    if (h == 4 && w == 4) return launch_tc<4, 4, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     return NFB_ERR_UNSUPPORTED;
 }
 
-static int tc_groups() {
-    const int G = g_tune[5];  // accumulator groups per layer (developer knob); 0 = default
-    return G >= 1 && G <= 4 ? G : 3;
-}
-
 int convnet_tc_dispatch(const float* zsrc, float* out, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
-                        int B, int h, int w, cudaStream_t st) {
-    const int G = tc_groups();
+                        int B, int h, int w, int flags, cudaStream_t st) {
     if (mode == NFB_SPLIT_CHECKER)
-        return tc_by_size<NFB_SPLIT_CHECKER, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
+        return tc_by_size<NFB_SPLIT_CHECKER, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, flags, st);
     if (mode == NFB_SPLIT_CHANNEL)
-        return tc_by_size<NFB_SPLIT_CHANNEL, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
-    return tc_by_size<-1, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, G, st);
+        return tc_by_size<NFB_SPLIT_CHANNEL, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, flags, st);
+    return tc_by_size<-1, false>(zsrc, out, nullptr, pk_tc, g, Cin, Cout, B, h, w, nullptr, nullptr, flags, st);
 }
 
 int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout, int B,
-                               const float* sa, const float* sb, cudaStream_t st) {
-    const int G = tc_groups();
+                               const float* sa, const float* sb, int flags, cudaStream_t st) {
     if (Cout != 2 * g.c0) return NFB_ERR_SHAPE;
     if (mode == NFB_SPLIT_CHECKER)
-        return tc_by_size<NFB_SPLIT_CHECKER, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, G, st);
+        return tc_by_size<NFB_SPLIT_CHECKER, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, flags, st);
     if (mode == NFB_SPLIT_CHANNEL)
-        return tc_by_size<NFB_SPLIT_CHANNEL, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, G, st);
+        return tc_by_size<NFB_SPLIT_CHANNEL, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, g.h, g.w, sa, sb, flags, st);
     return NFB_ERR_UNSUPPORTED;
 }
 

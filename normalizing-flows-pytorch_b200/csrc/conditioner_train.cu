@@ -279,11 +279,7 @@ static int launch_conv_layer(const ConvArgs& A, cudaStream_t st) {
     constexpr int S = (NT / (kF / OCT)) / (H * W / 4);
     constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 32 * KS * KS * 32) * sizeof(float);
     auto kern = conv_layer_kernel<H, W, NT, OCT, KS, TILES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     kern<<<TILES == 1 ? (A.B + S - 1) / S : A.B * TILES, NT, smem, st>>>(A);
     return launch_status();
 }
@@ -737,12 +733,8 @@ extern "C" int nfb_conv_train_wgrad(const float* gy, const float* a, float* gw, 
 #define NFB_WG(H_, W_, SPI_, TILES_)                                                                         \
     do {                                                                                                     \
         constexpr size_t smem = sizeof(float) * 32 * ((SPI_) * (H_) * (W_) + 4 + (SPI_) * ((H_) + 2) * (W_) + 4); \
-        static bool attr_set = false;                                                                        \
-        if (!attr_set) {                                                                                     \
-            cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3, SPI_, TILES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+                    cudaFuncSetAttribute(wgrad_kernel<H_, W_, 3, SPI_, TILES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
             cudaFuncSetAttribute(wgrad_kernel<H_, W_, 1, SPI_, TILES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-            attr_set = true;                                                                                 \
-        }                                                                                                    \
         if (ks == 3) wgrad_kernel<H_, W_, 3, SPI_, TILES_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, units, spc); \
         else wgrad_kernel<H_, W_, 1, SPI_, TILES_><<<grid, 256, smem, st>>>(gy, a, scratch, Cin, Cout, units, spc); \
         rc = launch_status();                                                                                \

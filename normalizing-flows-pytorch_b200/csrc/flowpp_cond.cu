@@ -378,11 +378,7 @@ static int launch_fpp(const float* zsrc, float* out, const FppArgs& A, const Spl
     constexpr int S = (NT / (kF / OCT)) / (H * W / 4);
     constexpr size_t smem = (static_cast<size_t>(kF) * S * (H + 2) * W + 2 * kWStage) * sizeof(float);
     auto kern = flowpp_cond_kernel<H, W, NT, OCT, MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     kern<<<(B + S - 1) / S, NT, smem, st>>>(zsrc, out, A, g, Cin, Cout, B);
     return launch_status();
 }

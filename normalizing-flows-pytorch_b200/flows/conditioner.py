@@ -35,6 +35,9 @@ class _ResBlock(nn.Module):
 
 class _ResNetConditioner(nn.Module):
     conv = False
+    # kernel selection of the fused ConvNet (flags of nfb_convnet_fwd_ex; 0 = default: tensor-core kernel).  A per-module
+    # attribute, not library state: tests and the profiling scripts set it on the instance they measure.
+    kernel_flags = 0
 
     def __init__(self, in_channels, out_channels, base_filters=32, n_blocks=2, weight_norm=True):
         super().__init__()
@@ -102,8 +105,8 @@ class _ResNetConditioner(nn.Module):
         if self.conv:
             h, w = x.size(2), x.size(3)
             out = torch.empty((B, self.out_channels, h, w), device=x.device, dtype=torch.float32)
-            rc = L.lib().nfb_convnet_fwd(L.ptr(x), L.ptr(out), L.ptr(self.packed()), B, 0, h, w, -1, 0,
-                                         self.in_channels, self.out_channels, L.stream())
+            rc = L.lib().nfb_convnet_fwd_ex(L.ptr(x), L.ptr(out), L.ptr(self.packed()), B, 0, h, w, -1, 0,
+                                            self.in_channels, self.out_channels, int(self.kernel_flags), L.stream())
             if rc == L.ERR_UNSUPPORTED:
                 return self._forward_library(x)
         else:
@@ -122,8 +125,8 @@ class _ResNetConditioner(nn.Module):
             _, C, H, W = z.shape
             h, w = (H // 2, W // 2) if mode == L.SPLIT_CHECKER else (H, W)
             out = torch.empty((B, self.out_channels, h, w), device=z.device, dtype=torch.float32)
-            rc = L.lib().nfb_convnet_fwd(L.ptr(z), L.ptr(out), L.ptr(self.packed()), B, C, H, W, mode, int(odd),
-                                         self.in_channels, self.out_channels, L.stream())
+            rc = L.lib().nfb_convnet_fwd_ex(L.ptr(z), L.ptr(out), L.ptr(self.packed()), B, C, H, W, mode, int(odd),
+                                            self.in_channels, self.out_channels, int(self.kernel_flags), L.stream())
             if rc == L.ERR_UNSUPPORTED:
                 return None
         else:

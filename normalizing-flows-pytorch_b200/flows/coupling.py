@@ -121,7 +121,7 @@ class AffineCoupling(AbstractCoupling):
         out = z if inplace else z.clone()
         rc = L.lib().nfb_convnet_affine_fwd(L.ptr(out), L.ptr(ldj), L.ptr(self.net.packed()),
                                             L.ptr(self.s_log_scale.data), L.ptr(self.s_bias.data), B, C, H, W, self.mode,
-                                            int(self.odd), L.stream())
+                                            int(self.odd), int(self.net.kernel_flags), L.stream())
         if rc == L.ERR_UNSUPPORTED:
             return None
         L.check(rc)

@@ -234,29 +234,11 @@ def _invconv_actnorm_inv(an, conv, y, log_df_dz):
     return out, log_df_dz
 
 
-def _glow_step(an, conv, cpl, z, log_df_dz):
-    """ActNorm -> InvertibleConv1x1 -> AffineCoupling (ConvNet conditioner) as ONE launch; None if not applicable."""
-    from .coupling import AffineCoupling
-    if type(cpl) is not AffineCoupling or len(cpl.dims) != 3 or cpl.net.training:
-        return None
-    z, log_df_dz = L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz')
-    B, C, H, W = z.shape
-    out = torch.empty_like(z)
-    rc = L.lib().nfb_glow_step_fwd(L.ptr(z), L.ptr(out), L.ptr(log_df_dz), L.ptr(log_df_dz), L.ptr(an.log_scale.data),
-                                   L.ptr(an.bias.data), L.ptr(conv.matrices()[0]), L.ptr(conv.log_s.data),
-                                   L.ptr(cpl.net.packed()), L.ptr(cpl.s_log_scale.data), L.ptr(cpl.s_bias.data), B, C, H,
-                                   W, cpl.mode, int(cpl.odd), L.stream())
-    if rc == L.ERR_UNSUPPORTED:
-        return None
-    L.check(rc)
-    return out, log_df_dz
-
-
 class Compose(nn.Module):
     """modules.py:325-339: sequential / reversed application."""
 
-    # 0: every layer its own kernel; 1: ActNorm+1x1conv fused (default); 2: whole Glow steps as one launch
-    # (nfb_glow_step_fwd: correct, but measured slower than 1 on B200 -- its prologue/epilogue run at conv-kernel occupancy)
+    # 1 (default): a Glow step is two launches -- ActNorm + 1x1 conv, then the tensor-core conditioner with the affine
+    # coupling as its epilogue, in place on the 1x1 conv's output; 0: every layer through its own forward()
     fuse_steps = 1
 
     def __init__(self, layers):
@@ -272,16 +254,9 @@ class Compose(nn.Module):
         owned = False  # z is a tensor produced inside this loop (safe to update in place)
         while i < n:
             layer = layers[i]
-            # peepholes (same arithmetic, fewer launches): a whole Glow step ActNorm -> 1x1 conv -> AffineCoupling as one
-            # kernel; else an initialised ActNorm followed by the 1x1 convolution as one kernel
+            # peepholes (same arithmetic, fewer launches): an initialised ActNorm followed by the 1x1 convolution as one kernel
             if (i + 1 < n and type(layer) is ActNorm and layer.initialized and type(layers[i + 1]) is InvertibleConv1x1
                     and fuse):
-                if i + 2 < n and fuse > 1:
-                    out = _glow_step(layer, layers[i + 1], layers[i + 2], z, log_df_dz)
-                    if out is not None:
-                        z, log_df_dz = out
-                        i += 3
-                        continue
                 out = _actnorm_invconv(layer, layers[i + 1], z, log_df_dz)
                 if out is not None:
                     z, log_df_dz = out

@@ -31,10 +31,6 @@ def perturb_(m, seed):
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
 
 
-def tune(k, v):
-    L.check(L.lib().nfb_set_tuning(k, v))
-
-
 def timeit(fn, n=20):
     for _ in range(3):
         fn()
@@ -64,34 +60,32 @@ def convnet_case(cin, cout, hw, B, groups=(3, 1)):
     for p_ in net.parameters():
         p_.requires_grad_(False)
     xd = x.to(DEV)
-    tune(3, 2)
+    net.kernel_flags = L.CONV_FFMA
     ffma = net(xd)
     t_ff = timeit(lambda: net(xd))
-    tune(3, 0)
+    net.kernel_flags = 0
     scale = float(ref64.abs().max())
     e_ff = float((ffma[:nref].cpu().double() - ref64).abs().max())
     e_32 = float((ref32.double() - ref64).abs().max())
     line = 'convnet cin=%3d cout=%3d %2dx%-2d B=%4d | scale %.2f | cpu32 %.2e ffma %.2e (%.1f us)' % (
         cin, cout, hw, hw, B, scale, e_32, e_ff, t_ff)
     for G in groups:
-        tune(5, G)
+        net.kernel_flags = L.conv_groups(G)
         tc = net(xd)
         torch.cuda.synchronize()
         e_tc = float((tc[:nref].cpu().double() - ref64).abs().max())
         d_all = float((tc - ffma).abs().max())
         t_tc = timeit(lambda: net(xd))
         line += ' | G=%d tc %.2e, vs ffma(all) %.2e (%.1f us)' % (G, e_tc, d_all, t_tc)
-    tune(5, 0)
+    net.kernel_flags = 0
     print(line, flush=True)
     if B == 256:
         line = '    knobs (us):'
         for G in (3, 1):
-            tune(5, G)
-            for dbg in (0, 1, 2, 4, 8, 16, 32, 1 | 2, 1 | 2 | 16, 1 | 2 | 16 | 32, 2 | 16):
-                tune(4, dbg)
+            for dbg in (0, 1, 2, 4, 16, 32, 1 | 2, 1 | 2 | 16, 1 | 2 | 16 | 32, 2 | 16):
+                net.kernel_flags = L.conv_groups(G) | L.conv_debug(dbg)
                 line += ' G%d/%d=%.1f' % (G, dbg, timeit(lambda: net(xd)))
-        tune(4, 0)
-        tune(5, 0)
+        net.kernel_flags = 0
         print(line, flush=True)
 
 
@@ -111,10 +105,10 @@ def fused_case(dims, masking, odd, B):
         cpl.fused_conditioner = False
         z2, l2 = cpl(x, l0.clone())          # tensor-core conditioner + coupling kernel
         t_2 = timeit(lambda: cpl(x, l0.clone()))
-        tune(3, 2)
+        cpl.net.kernel_flags = L.CONV_FFMA
         z3, l3 = cpl(x, l0.clone())          # FFMA conditioner + coupling kernel
         t_3 = timeit(lambda: cpl(x, l0.clone()))
-        tune(3, 0)
+        cpl.net.kernel_flags = 0
     print('fused %s %s odd=%d B=%d | z: fused-vs-2k %.2e, fused-vs-ffma %.2e | ldj %.2e / %.2e | fused %.1f us (clone %.1f) '
           '2-kernel %.1f us, ffma 2-kernel %.1f us' %
           (dims, masking, odd, B, float((z1 - z2).abs().max()), float((z1 - z3).abs().max()),

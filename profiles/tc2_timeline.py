@@ -20,10 +20,9 @@ buf = torch.zeros(3 * 512, dtype=torch.int64, device='cuda:0')
 fn = L.lib().nfb_debug_timeline
 fn.argtypes = [ctypes.c_void_p]
 fn(buf.data_ptr())
-L.lib().nfb_set_tuning(4, dbg)
+net.kernel_flags = L.conv_debug(dbg)
 net(x)
 torch.cuda.synchronize()
-L.lib().nfb_set_tuning(4, 0)
 fn(None)
 ev = buf.cpu().view(3, 512)
 NAMES = {1: 'mma wait w_full', 2: 'mma got w_full', 10: 'mma wait act0', 11: 'mma wait act1', 12: 'mma got act0', 13: 'mma got act1',

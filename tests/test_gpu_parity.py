@@ -435,12 +435,9 @@ def test_convnet_variants_agree(key, values, cin, cout, hw):
     net = F.ConvNet(cin, cout).to(DEV).eval()
     x = torch.randn(37, cin, hw, hw, device=DEV)
     outs = []
-    try:
-        for v in values:
-            L.check(L.lib().nfb_set_tuning(key, v))
-            outs.append(net(x))
-    finally:
-        L.lib().nfb_set_tuning(key, 0)
+    for v in values:
+        net.kernel_flags = L.CONV_FFMA | L.conv_variant(v)
+        outs.append(net(x))
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
 
@@ -461,13 +458,11 @@ def test_convnet_tensor_core_path(cin, cout, hw, B):
         ref = O.resnet_conditioner(sd, '', x[:8])
         ref64 = O.resnet_conditioner(O.to_dtype(sd, torch.float64), '', x[:8].double())
     net.to(DEV)
+    net.kernel_flags = L.CONV_FFMA
     ffma = net(x.to(DEV))
-    try:
-        L.check(L.lib().nfb_set_tuning(3, 1))
-        tc = net(x.to(DEV))
-        torch.cuda.synchronize()
-    finally:
-        L.lib().nfb_set_tuning(3, 0)
+    net.kernel_flags = 0
+    tc = net(x.to(DEV))
+    torch.cuda.synchronize()
     scale = max(1.0, float(ref.abs().max()))
     e_tc = float((tc[:8].cpu().double() - ref64).abs().max())
     e_ff = float((ffma[:8].cpu().double() - ref64).abs().max())
@@ -479,31 +474,46 @@ def test_convnet_tensor_core_path(cin, cout, hw, B):
 
 @pytest.mark.parametrize('dims,masking', [((3, 32, 32), 'checkerboard'), ((12, 16, 16), 'channelwise'),
                                           ((12, 16, 16), 'checkerboard'), ((48, 8, 8), 'channelwise'),
-                                          ((48, 8, 8), 'checkerboard')])
+                                          ((48, 8, 8), 'checkerboard'), ((6, 8, 8), 'channelwise'),
+                                          ((2, 8, 8), 'checkerboard'), ((96, 16, 16), 'channelwise'),
+                                          ((192, 8, 8), 'checkerboard')])
 @pytest.mark.parametrize('odd', [False, True])
-@pytest.mark.parametrize('B', [3, 256])
-def test_fused_glow_step_matches_separate_layers(dims, masking, odd, B):
-    """One-launch flow step (ActNorm -> 1x1 conv -> AffineCoupling) vs the three layers run separately: z identical
-    except for the reduction order of the log-det (block sum vs warp sums)."""
+@pytest.mark.parametrize('B', [1, 3, 19, 256])
+def test_fused_conditioner_coupling(dims, masking, odd, B):
+    """nfb_convnet_affine_fwd (conditioner on the tensor cores + affine coupling + log-det in ONE kernel, in place) vs the
+    two-kernel path (nfb_convnet_fwd_ex + nfb_affine_coupling_fwd): same arithmetic -> identical z; the pass-through half is
+    bit-identical to the input; the log-det differs only by the reduction order; and both agree with the FFMA conditioner."""
     n = nfb()
+    import nfb200._lib as L
     torch.manual_seed(7)
-    an, conv = n.flows.ActNorm(dims), n.flows.InvertibleConv1x1(dims[0])
     cpl = n.flows.AffineCoupling(dims, masking=masking, odd=odd)
-    for m_, sd_ in ((an, 1), (conv, 2), (cpl, 3)):
-        perturb_(m_, sd_)
-    an.initialized = True
-    comp = n.flows.Compose([an, conv, cpl]).to(DEV).eval()
+    perturb_(cpl, 3)
+    cpl.to(DEV).eval()
     x = torch.randn((B, ) + dims, device=DEV)
     l0 = torch.randn(B, device=DEV)
-    comp.fuse_steps = 2
-    comp(x, l0.clone())  # first call packs the conditioner weights / builds W (one-time launches)
+    x_keep = x.clone()
     n0 = n._lib.launch_count()
-    z1, l1 = comp(x, l0.clone())
-    assert n._lib.launch_count() - n0 == 1  # ONE kernel for the whole step
-    comp.fuse_steps = 0
-    z2, l2 = comp(x, l0.clone())
+    cpl(x, l0.clone())  # first call packs the conditioner weights (one-time launches)
+    n0 = n._lib.launch_count()
+    z1, l1 = cpl(x, l0.clone())
+    assert n._lib.launch_count() - n0 == 1  # ONE libnfb200 kernel for conditioner + coupling
+    assert torch.equal(x, x_keep)           # the layer API leaves its input alone
+    z1b, l1b = cpl.forward_fused(x.clone(), l0.clone(), inplace=True)
+    assert torch.equal(z1, z1b) and torch.equal(l1, l1b)
+    cpl.fused_conditioner = False
+    z2, l2 = cpl(x, l0.clone())
     assert torch.equal(z1, z2)
     close(l1, l2, rtol=1e-6, atol=1e-4, what='ldj')
+    # pass-through half untouched
+    m = n.flows.squeeze
+    _, z1_in = m.coupling_split(x, cpl.mode, cpl.odd, want_z0=False)
+    _, z1_out = m.coupling_split(z1, cpl.mode, cpl.odd, want_z0=False)
+    assert torch.equal(z1_in, z1_out)
+    cpl.net.kernel_flags = L.CONV_FFMA
+    z3, l3 = cpl(x, l0.clone())
+    scale = max(1.0, float(z3.abs().max()))
+    close(z1, z3, rtol=2e-5, atol=4e-6 * scale, what='tensor-core vs ffma conditioner')
+    close(l1, l3, rtol=2e-5, atol=4e-6 * max(1.0, float(l3.abs().max())), what='ldj tensor-core vs ffma')
 
 
 # ---------------------------------------------------------------------------------------------------------
