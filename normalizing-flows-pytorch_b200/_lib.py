@@ -153,6 +153,28 @@ def launch_count():
     return int(lib().nfb_launch_count())
 
 
+# Conditioner calls that left libnfb200 for torch ops (cuDNN / cuBLAS): spatial sizes or modes without a native kernel.
+# Nothing is silent: nfb200.library_path_calls() reports the count, bench.py prints it (0 on the BASELINE configs), and
+# NFB200_STRICT=1 turns every such call into an error.
+_library_calls = [0]
+_library_log = {}
+
+
+def note_library_path(what):
+    _library_calls[0] += 1
+    _library_log[what] = _library_log.get(what, 0) + 1
+    if os.environ.get('NFB200_STRICT') == '1':
+        raise RuntimeError('nfb200: %s would run on cuDNN / cuBLAS torch ops (NFB200_STRICT=1)' % what)
+
+
+def library_path_calls():
+    return _library_calls[0]
+
+
+def library_path_log():
+    return dict(_library_log)
+
+
 def empty_batch(t):
     """B == 0: nothing to launch (the reference returns empty tensors); the C ABI itself rejects B <= 0."""
     return t.numel() == 0

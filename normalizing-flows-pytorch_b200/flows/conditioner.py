@@ -150,6 +150,7 @@ class _ResNetConditioner(nn.Module):
         return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
 
     def _forward_library(self, x):
+        L.note_library_path('%s eval forward at %s' % (type(self).__name__, tuple(x.shape[2:])))
         x = L.dev(x, 'conditioner input')
         with torch.no_grad():
             x = self._layer(self.in_block[0], x)
@@ -209,6 +210,8 @@ class _ResNetConditioner(nn.Module):
         out = self._forward_native_train(x)
         if out is not None:
             return out
+        L.note_library_path('%s %s forward under autograd at %s' % (type(self).__name__, 'train' if self.training else 'eval',
+                                                                   tuple(x.shape[1:])))
         x = self._wn_apply(self.in_block[0], x)
         for blk in self.mid_block:
             y = F.relu(blk.net[0](x))

@@ -228,6 +228,7 @@ class MixLogAttnCoupling(AbstractCoupling):
                 L.check(rc)
                 return out
         # library path (torch ops on the device): spatial sizes the kernels do not cover, train mode
+        L.note_library_path('Flow++ conditioner %s at %s' % ('train' if self.net.training else 'eval', tuple(z.shape[1:])))
         z1 = self._z1(z)
         return L.dev(self.net(z1), 'conditioner output')
 

@@ -1,7 +1,8 @@
 """Eager (no CUDA graph) steps of a bench workload, for ncu launch lists / full captures.
 
-    ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c <n> --csv --log-file out.csv \
+    ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
         python profiles/glow_step.py [workload] [steps]
+(the profiled range -- cudaProfilerStart/Stop -- is the steps after the initialising forward)
 """
 import os
 import sys
@@ -24,8 +25,10 @@ with torch.no_grad():
     net(x)  # ActNorm init + weight packing (skipped with ncu -s)
     torch.cuda.synchronize()
     n0 = nfb200._lib.launch_count()
+    torch.cuda.cudart().cudaProfilerStart()
     for _ in range(steps):
         z, ldj = net(x)
         rows, total = nfb200.gauss_nll(z, ldj)
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
 print('launches per step', (nfb200._lib.launch_count() - n0) // steps, 'bpd', nfb200.bits_per_dim_from_total(total, x[0].numel()))
