@@ -428,8 +428,11 @@ class Harness:
             nfb200.gauss_nll(z, ldj)
             self.launches_per_step = nfb200._lib.launch_count() - n0
             torch.cuda.synchronize()
+            # several batches in flight: two tiles per CTA on the 8x8 / 4x4 conditioner maps (nfb200.set_throughput_mode);
+            # the extra last lane is captured in latency mode and serves the single-stream leg
             self.lanes = []
-            for k in range(n_lanes):
+            for k in range(n_lanes + (1 if n_lanes > 1 else 0)):
+                nfb200.set_throughput_mode(n_lanes > 1 and k < n_lanes)
                 st = torch.cuda.Stream()
                 x_static = self.dev_ring[0].clone()
                 st.wait_stream(torch.cuda.current_stream())
@@ -445,6 +448,8 @@ class Harness:
                 self.lanes.append(dict(stream=st, x=x_static, graph=graph, rows=rows, total=total,
                                        host_total=torch.zeros(2, dtype=torch.float64).pin_memory(),
                                        host_rows=torch.zeros(batch, dtype=torch.float32).pin_memory()))
+            nfb200.set_throughput_mode(False)
+            self.latency_lane = self.lanes.pop() if n_lanes > 1 else self.lanes[0]
             torch.cuda.synchronize()
 
     def timed(self, steps, warmup, lanes_used, host_inputs, read_back):
@@ -453,7 +458,7 @@ class Harness:
         all-reduced ONCE after the last step, inside the timed region; result = max over ranks."""
         import torch.distributed as dist
         src_ring = self.host_ring if host_inputs else self.dev_ring
-        lanes, world = self.lanes, self.world
+        lanes, world = (self.lanes if lanes_used > 1 else [self.latency_lane]), self.world
         totals = torch.zeros(steps + warmup, 2, device=self.dev, dtype=torch.float64)
         host_totals = torch.zeros(steps + warmup, 2, dtype=torch.float64).pin_memory()
 
@@ -511,7 +516,7 @@ class Harness:
     def bits_per_dim_ring0(self):
         import nfb200
         from nfb200 import parallel
-        ln = self.lanes[0]
+        ln = self.latency_lane
         with torch.no_grad():
             ln['x'].copy_(self.dev_ring[0])
             ln['graph'].replay()
@@ -610,7 +615,7 @@ def run_nfb200(args, rank, world, local_rank):
         t_end = time.perf_counter() + 1.0
         with torch.no_grad():
             while time.perf_counter() < t_end:
-                H.lanes[0]['graph'].replay()
+                H.lanes[0]['graph'].replay()  # local work only
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     value = batch * world * args.steps / (ms * 1e-3)
@@ -623,7 +628,7 @@ def run_nfb200(args, rank, world, local_rank):
     try:
         with torch.no_grad():
             zs = torch.randn_like(H.dev_ring[0])
-            st = H.lanes[0]['stream']
+            st = H.latency_lane['stream']
             with torch.cuda.stream(st):
                 for _ in range(2):
                     H.net.backward(zs)
@@ -704,6 +709,8 @@ def run_nfb200(args, rank, world, local_rank):
         'run': {'l2': 'inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)' % (ring_n, ring_n * bytes_per_batch / 1e6),
                 'parallelism': 'sample-sharded replicas x%d; one all-reduce of K x (sum NLL, count) per timed window' % world,
                 'batches_in_flight': n_lanes,
+                'kernel_selection': 'throughput mode (nfb200.set_throughput_mode: two tiles per CTA on 8x8 / 4x4 conditioner maps) '
+                                    'for the %d-lane legs; latency mode for single_stream and inverse' % n_lanes,
                 'timing': 'CUDA events around K graph replays (%d batches in flight on %d streams), max over ranks' % (n_lanes, n_lanes),
                 'wall_s': wall},
         'single_stream': {'value': value_single, 'ms_per_step': ms_single / args.steps,

@@ -203,9 +203,13 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
  *   NFB_CONV_FFMA            use the FP32-FFMA kernels
  *   NFB_CONV_VARIANT_MASK    thread-tile variant of the FP32-FFMA kernel for this spatial size (0 = default)
  *   NFB_CONV_GROUPS(g)       accumulator groups per layer of the tensor-core kernel, 1..4 (0 = default 3)
+ *   NFB_CONV_PAIR            8x8 / 4x4 maps: two independent 128-position tiles per CTA taking turns on the tensor core
+ *                            (more work per SM-second, half the CTAs): for several batches in flight; without the flag
+ *                            it is chosen only when the batch alone gives every SM two tiles
  *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results */
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
+#define NFB_CONV_PAIR 0x80
 #define NFB_CONV_GROUPS_SHIFT 4
 #define NFB_CONV_GROUPS(g) ((g) << NFB_CONV_GROUPS_SHIFT)
 #define NFB_CONV_DEBUG_SHIFT 8

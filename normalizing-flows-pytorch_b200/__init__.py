@@ -6,7 +6,7 @@ The directory is named ``normalizing-flows-pytorch_b200`` (not an importable ide
 shim package at the repo root) is the supported import name.
 """
 from . import _lib, flows, likelihood, parallel  # noqa: F401
-from .flows import Flowpp, Glow, RealNVP  # noqa: F401
+from .flows import Flowpp, Glow, RealNVP, set_throughput_mode  # noqa: F401
 from .likelihood import bits_per_dim_from_total, gauss_nll  # noqa: F401
 from ._lib import library_path_calls, library_path_log  # noqa: F401
 

@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'nfb200.h')
 SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
 # kernel selection flags of nfb_convnet_fwd_ex / nfb_convnet_affine_fwd (include/nfb200.h)
 CONV_FFMA = 0x8
+CONV_PAIR = 0x80
 
 
 def conv_variant(v):
@@ -161,10 +162,19 @@ _library_log = {}
 
 
 def note_library_path(what):
+    """Called by every conditioner path that runs on torch ops (cuDNN / cuBLAS) instead of libnfb200 kernels.  The 1e-5
+    bits/dim bar rules out TF32, and cuDNN's backward reads the global switch when it runs, so the first
+    such call turns TF32 off for the process -- announced once; importing the package alone changes nothing."""
     _library_calls[0] += 1
     _library_log[what] = _library_log.get(what, 0) + 1
     if os.environ.get('NFB200_STRICT') == '1':
         raise RuntimeError('nfb200: %s would run on cuDNN / cuBLAS torch ops (NFB200_STRICT=1)' % what)
+    if torch.backends.cudnn.allow_tf32 or torch.backends.cuda.matmul.allow_tf32:
+        import warnings
+        warnings.warn('nfb200: %s runs on cuDNN / cuBLAS torch ops; switching torch.backends.{cudnn,cuda.matmul}.allow_tf32 '
+                      'off for this process (fp32 parity with the reference)' % what, stacklevel=3)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def library_path_calls():
@@ -173,6 +183,26 @@ def library_path_calls():
 
 def library_path_log():
     return dict(_library_log)
+
+
+# Derived-weight caches (folded conditioner weights, W / W^-1 of the 1x1 convolutions, WeightNorm folds) are keyed on the
+# parameters' (data_ptr, _version) AND on this epoch: parameter updates that do not bump _version -- CUDA-graph replays of
+# an optimizer step (parallel.GraphedTrainStep), raw pointer writes -- call bump_weights_epoch() so that the next forward
+# re-derives everything.
+_weights_epoch = [0]
+
+
+def weights_epoch():
+    return _weights_epoch[0]
+
+
+def bump_weights_epoch():
+    _weights_epoch[0] += 1
+
+
+def param_key(tensors):
+    """Cache key of derived weights: storage identity + in-place version of every source tensor + the global epoch."""
+    return (_weights_epoch[0], ) + tuple((t.data_ptr(), t._version) for t in tensors)
 
 
 def empty_batch(t):

@@ -31,6 +31,7 @@
 //            the plain params store.
 // 16x16: the two tiles of a sample overlap (epilogue of one under the MMAs of the other); the in-place activation
 // update is ordered by a "halo-free" commit after the second tile's dy = -1 taps.
+#include <cstdio>
 #include <utility>
 
 #include "conditioner.cuh"
@@ -74,7 +75,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// site: who waits (for the time-out report): 1 producer, 2.. MMA lane, 30.. epilogue (which waits 2 s longer, so that
+// the role that is actually stuck reports first)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
     // bounded (4 s of wall clock): a lost arrival must trap (cudaErrorLaunchFailure), never hang the GPU
     if (mbar_try(bar, parity)) return;
     unsigned long long t0, t1;
@@ -84,7 +87,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         for (int it = 0; it < 64; ++it)
             if (mbar_try(bar, parity)) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) __trap();
+        if (t1 - t0 > (site >= 30 ? 6000000000ull : 4000000000ull)) {
+            printf("nfb200 convnet_tc_kernel: mbarrier %u (parity %u) timed out at site %d: block %d thread %d\n", bar, parity,
+                   site, static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));
+            __trap();
+        }
     }
 }
 // TMA (bulk async copy engine): global -> shared, completion counted in bytes on an mbarrier
@@ -185,6 +192,28 @@ __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[16 + i]);
+    }
+}
+
 // K-major, no swizzle: start address, leading (K-chunk) and stride (8-row group) byte offsets, all in 16-byte units
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -234,7 +263,7 @@ __device__ __forceinline__ int half_elem_offset(const SplitGeom& g, int m, int s
 }
 
 // developer timeline: when set (nfb_debug_timeline), CTA 0 records clock64() stamps: [role 0 = epilogue thread 0,
-// 1 = epilogue thread 128, 2 = MMA lane 0][event index] = (tag << 48) | (clock & 0xffffffffffff)
+// 1 = epilogue thread 128, 2 = MMA lane 0, 3 = kernel entry / prologue done / exit][event index] = (tag << 48) | (clock & 0xffffffffffff)
 __device__ unsigned long long* g_tl_buf = nullptr;
 constexpr int kTlEvents = 512;
 struct Timeline {
@@ -260,12 +289,17 @@ constexpr int kEpiThreads = 256;
 constexpr int kThreads = 320;
 constexpr int kTileCols = 256;            // TMEM columns reserved per tile
 
-template <int H, int W>
+// PAIR (maps of <= 128 pixels only): a unit is TWO independent tiles that take turns on the tensor core exactly like the
+// two tiles of a 16x16 sample (epilogue of one under the MMAs of the other, weights streamed once for both): ~1.5x the
+// work per SM-second of the single-tile unit, which leaves the tensor core idle during every epilogue, at the price of
+// half as many CTAs -- the choice when the batch (or several batches in flight) fills the machine anyway.
+template <int H, int W, bool PAIR>
 struct TcGeom {
     static constexpr int HW = H * W;
-    static constexpr bool LINKED = HW > 128;            // a sample spans several tiles (16x16: 2)
-    static constexpr int T = LINKED ? HW / 128 : 1;     // tiles per unit
-    static constexpr int SPU = LINKED ? 1 : 128 / HW;   // samples per unit
+    static constexpr bool LINKED = HW > 128 || PAIR;    // two tiles per unit, ping-pong (16x16: the two halves of a sample)
+    static constexpr int T = LINKED ? 2 : 1;            // tiles per unit
+    static constexpr int SPT = HW > 128 ? 0 : 128 / HW; // samples per tile (0: a sample spans both tiles)
+    static constexpr int SPU = HW > 128 ? 1 : T * SPT;  // samples per unit
     static constexpr int CS = LINKED ? 1 : 2;           // epilogue warps per TMEM lane quarter of one tile
     static constexpr int NCH = 32 / CS;                 // channels per epilogue thread
     static constexpr int GUARD = (W + 1 + 3) & ~3;      // positions before / after the tiles (tap offsets reach there)
@@ -274,6 +308,7 @@ struct TcGeom {
     static constexpr int ACT_BYTES = 16 * PS;           // 8 hi planes + 8 lo planes
     static_assert(T <= 2 && T * kTileCols <= 512, "unit exceeds TMEM");
     static_assert(HW == 256 || 128 % HW == 0, "tile must hold whole samples");
+    static_assert(!(PAIR && HW > 128), "PAIR is for maps of at most 128 pixels");
 };
 
 }  // namespace
@@ -281,13 +316,13 @@ struct TcGeom {
 // =====================================================================================================================
 // the kernel
 // =====================================================================================================================
-template <int H, int W, int MODE, bool FUSED>
+template <int H, int W, int MODE, bool FUSED, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
                   int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, int G, int dbg) {
-    using GM = TcGeom<H, W>;
-    constexpr int HW = GM::HW, T = GM::T, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD, PB = GM::PB,
-                  PS = GM::PS;
+    using GM = TcGeom<H, W, PAIR>;
+    constexpr int HW = GM::HW, T = GM::T, SPT = GM::SPT, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD,
+                  PB = GM::PB, PS = GM::PS;
     constexpr bool LINKED = GM::LINKED;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* act = smem_raw;                              // [16 planes][PB][16 B]
@@ -307,6 +342,9 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Timeline tl_k;  // kernel entry / prologue done / exit (globaltimer ns in the low bits for tags >= 60)
+    tl_k.init(3, blockIdx.x == 0 && tid == 0);
+    tl_k.stamp(0);
     const int NW = FUSED ? P.NWf : P.NWg, nq = FUSED ? P.nqf : P.nqg;
     const int out_chunk_bytes = 256 * NW;
     const int qps = kSlotBytes / out_chunk_bytes;               // out chunks per weight stage
@@ -363,6 +401,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    tl_k.stamp(1);
 
     if (warp == 9) {
         // =============================== TMA producer ================================================================
@@ -372,7 +411,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 for (int s = 0; s < n_stage; ++s, ++cnt) {
                     const uint32_t slot = cnt & 1u;
-                    mbar_wait(bar(W_EMPTY + slot), ((cnt >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar(W_EMPTY + slot), ((cnt >> 1) & 1u) ^ 1u, 1);
                     size_t off;
                     uint32_t bytes;
                     if (s < P.n_in) {
@@ -412,8 +451,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             tl.init(2, blockIdx.x == 0);
             auto wait_act = [&](int t) {
                 tl.stamp(10 + t);
-                if (t == 0) { mbar_wait(bar(ACT_READY), ph_act0); ph_act0 ^= 1u; }
-                else { mbar_wait(bar(ACT_READY + 1), ph_act1); ph_act1 ^= 1u; }
+                if (t == 0) { mbar_wait(bar(ACT_READY), ph_act0, 10); ph_act0 ^= 1u; }
+                else { mbar_wait(bar(ACT_READY + 1), ph_act1, 11); ph_act1 ^= 1u; }
                 tc_fence_after();
                 tl.stamp(12 + t);
             };
@@ -425,7 +464,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                 for (int s = 0; s < n_stage; ++s, ++cnt) {
                     const uint32_t slot = cnt & 1u;
                     tl.stamp(1);
-                    mbar_wait(bar(W_FULL + slot), (cnt >> 1) & 1u);
+                    mbar_wait(bar(W_FULL + slot), (cnt >> 1) & 1u, 2);
                     tc_fence_after();
                     tl.stamp(2);
                     const uint32_t wbase = smem_u32(ring + slot * kSlotBytes);
@@ -534,7 +573,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         const int ch0 = LINKED ? 0 : grp * NCH;          // first of this thread's NCH channels
         const int row = q4 * 32 + lane;                  // TMEM lane = position inside the tile
         const int pos = tile * 128 + row;                // position inside the unit
-        const int pix = LINKED ? pos : row % HW;
+        const int pix = HW > 128 ? pos : row % HW;
         const int yy = pix / W, xx = pix % W;
         const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(tile * kTileCols);
         const uint32_t b_acc = bar(ACC_DONE + tile), b_act = bar(ACT_READY + tile);
@@ -545,7 +584,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 
         auto wait_acc = [&]() {
             tl.stamp(30);
-            mbar_wait(b_acc, ph_acc);
+            mbar_wait(b_acc, ph_acc, 30);
             ph_acc ^= 1u;
             tc_fence_after();
             tl.stamp(31);
@@ -553,7 +592,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         auto wait_war = [&]() {
             if (LINKED && grp == 0) {
                 tl.stamp(32);
-                mbar_wait(bar(WAR0), ph_war);
+                mbar_wait(bar(WAR0), ph_war, 31);
                 ph_war ^= 1u;
                 tl.stamp(33);
             }
@@ -565,39 +604,40 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             mbar_arrive(b_act);
             tl.stamp(35);
         };
-        // v[c] = sum over the Ge accumulator groups of (main + compensation) for channels ch0 .. ch0+NCH-1
-        auto load_acc = [&](int Ge, float (&v)[NCH]) {
+        // The epilogue walks its NCH channels in sub-passes of EC = 16 (one for a column-split tile, two for a linked tile):
+        // 32 channels at once need ~130 live registers next to the 32 of the residual stream and spill (measured).
+        constexpr int EC = 16, NP = NCH / EC;
+        // v[c] = sum over the Ge accumulator groups of (main + compensation) for channels ch0 + sub*EC ... + EC - 1
+        auto load_acc = [&](int Ge, int sub, float (&v)[EC]) {
             if (dbg & 2) {  // profiling knob: no TMEM reads
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) v[i] = 0.f;
+                for (int i = 0; i < EC; ++i) v[i] = 0.f;
                 return;
             }
+            const uint32_t col = static_cast<uint32_t>(ch0 + sub * EC);
 #pragma unroll 1
             for (int gi = 0; gi < Ge; ++gi) {
-                float m[NCH];
-                tmem_ld<NCH>(t_lane + static_cast<uint32_t>(gi * 64 + ch0), m);
+                float m[EC], cp[EC];
+                tmem_ld16x2(t_lane + static_cast<uint32_t>(gi * 64) + col, t_lane + static_cast<uint32_t>(gi * 64 + 32) + col, m, cp);
                 if (gi == 0) {
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) v[i] = m[i];
+                    for (int i = 0; i < EC; ++i) v[i] = m[i] + cp[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) v[i] += m[i];
+                    for (int i = 0; i < EC; ++i) v[i] += m[i] + cp[i];
                 }
-                tmem_ld<NCH>(t_lane + static_cast<uint32_t>(gi * 64 + 32 + ch0), m);
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) v[i] += m[i];
             }
             tl.stamp(36);
         };
-        // a[NCH] (activated) -> hi / lo planes of this thread's position
-        auto store_act = [&](const float (&a)[NCH]) {
+        // a[EC] (activated) -> hi / lo planes of this thread's position
+        auto store_act = [&](int sub, const float (&a)[EC]) {
             if (dbg & 16) return;  // profiling knob: no activation stores
 #pragma unroll
-            for (int c4 = 0; c4 < NCH / 4; ++c4) {
+            for (int c4 = 0; c4 < EC / 4; ++c4) {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) split_tf32(a[c4 * 4 + q], hi[q], lo[q]);
-                const int plane = ch0 / 4 + c4;
+                const int plane = (ch0 + sub * EC) / 4 + c4;
                 st4(reinterpret_cast<float*>(my_act + plane * PS), make_float4(hi[0], hi[1], hi[2], hi[3]));
                 st4(reinterpret_cast<float*>(my_act + (8 + plane) * PS), make_float4(lo[0], lo[1], lo[2], lo[3]));
             }
@@ -613,7 +653,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             tl.stamp(40);
-            const int b = LINKED ? unit : unit * SPU + row / HW;
+            const int b = HW > 128 ? unit : unit * SPU + tile * SPT + row / HW;
             const bool valid = b < B;
             const float* zb = zsrc + static_cast<size_t>(b) * (MODE < 0 ? static_cast<size_t>(Cin) * HW : static_cast<size_t>(g.D));
             float xres[NCH];
@@ -623,8 +663,13 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             for (int c = 0; c < P.n_in; ++c) {
                 const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
                 const int n4 = ((CI + 7) & ~7) / 4;
-                for (int c4 = (CS == 2 ? grp : 0); c4 < n4; c4 += CS) {
-                    float hi[4], lo[4];
+                // this thread's share of the chunk: all loads first (they are independent: one round trip to L2), then the
+                // hi/lo split and the stores
+                constexpr int NG = 8 / CS;  // channel groups of 4 per thread
+                float gv[NG][4];
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    const int c4 = k * CS + (CS == 2 ? grp : 0);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int ci = c4 * 4 + q;
@@ -634,62 +679,99 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                             if (MODE < 0) v = __ldg(zb + cg * HW + pix);
                             else v = __ldg(zb + half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, cg, 1, yy, xx));
                         }
-                        split_tf32(v, hi[q], lo[q]);
+                        gv[k][q] = v;
                     }
-                    st4(reinterpret_cast<float*>(my_act + c4 * PS), make_float4(hi[0], hi[1], hi[2], hi[3]));
-                    st4(reinterpret_cast<float*>(my_act + (8 + c4) * PS), make_float4(lo[0], lo[1], lo[2], lo[3]));
+                }
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    const int c4 = k * CS + (CS == 2 ? grp : 0);
+                    if (c4 < n4) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) split_tf32(gv[k][q], hi[q], lo[q]);
+                        st4(reinterpret_cast<float*>(my_act + c4 * PS), make_float4(hi[0], hi[1], hi[2], hi[3]));
+                        st4(reinterpret_cast<float*>(my_act + (8 + c4) * PS), make_float4(lo[0], lo[1], lo[2], lo[3]));
+                    }
                 }
                 signal_act();
                 wait_acc();
                 const int nj = (c == P.n_in - 1) ? P.nj_last : 4;
-                float v[NCH];
-                load_acc(G < nj ? G : nj, v);
-                if (c == 0) {
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) xres[i] = v[i];
-                } else {
+                for (int sub = 0; sub < NP; ++sub) {
+                    float v[EC];
+                    load_acc(G < nj ? G : nj, sub, v);
+                    if (c == 0) {
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) xres[i] += v[i];
+                        for (int i = 0; i < EC; ++i) xres[sub * EC + i] = v[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < EC; ++i) xres[sub * EC + i] += v[i];
+                    }
                 }
                 wait_war();
             }
-            {
-                float a[NCH];
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    xres[i] += c_b0[ch0 + i];
-                    a[i] = fmaxf(fmaf(xres[i], c_blk(0, 0)[ch0 + i], c_blk(0, 1)[ch0 + i]), 0.f);
+            for (int sub = 0; sub < NP; ++sub) {
+                float a[EC];
+#pragma unroll
+                for (int i = 0; i < EC; ++i) {
+                    const int ch = ch0 + sub * EC + i;
+                    xres[sub * EC + i] += c_b0[ch];
+                    a[i] = fmaxf(fmaf(xres[sub * EC + i], c_blk(0, 0)[ch], c_blk(0, 1)[ch]), 0.f);
                 }
-                store_act(a);
-                signal_act();
+                store_act(sub, a);
             }
+            signal_act();
             // ---- two residual blocks ---------------------------------------------------------------------------------
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk) {
-                float v[NCH], a[NCH];
                 wait_acc();
-                load_acc(G < 4 ? G : 4, v);  // conv1 (second BatchNorm of the block folded into weights and bias)
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) a[i] = fmaxf(v[i] + c_blk(blk, 2)[ch0 + i], 0.f);
-                wait_war();
-                store_act(a);
+                for (int sub = 0; sub < NP; ++sub) {
+                    float v[EC], a[EC];
+                    load_acc(G < 4 ? G : 4, sub, v);  // conv1 (second BatchNorm of the block folded into weights and bias)
+#pragma unroll
+                    for (int i = 0; i < EC; ++i) a[i] = fmaxf(v[i] + c_blk(blk, 2)[ch0 + sub * EC + i], 0.f);
+                    if (sub == 0) wait_war();
+                    store_act(sub, a);
+                }
                 signal_act();
                 wait_acc();
-                load_acc(G < 4 ? G : 4, v);  // conv2 + skip
                 const float* sN = blk == 0 ? c_blk(1, 0) : c_sO;  // the BatchNorm that consumes the updated stream
                 const float* tN = blk == 0 ? c_blk(1, 1) : c_tO;
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    xres[i] += v[i] + c_blk(blk, 3)[ch0 + i];
-                    a[i] = fmaxf(fmaf(xres[i], sN[ch0 + i], tN[ch0 + i]), 0.f);
+                for (int sub = 0; sub < NP; ++sub) {
+                    float v[EC], a[EC];
+                    load_acc(G < 4 ? G : 4, sub, v);  // conv2 + skip
+#pragma unroll
+                    for (int i = 0; i < EC; ++i) {
+                        const int ch = ch0 + sub * EC + i;
+                        xres[sub * EC + i] += v[i] + c_blk(blk, 3)[ch];
+                        a[i] = fmaxf(fmaf(xres[sub * EC + i], sN[ch], tN[ch]), 0.f);
+                    }
+                    if (sub == 0) wait_war();
+                    store_act(sub, a);
                 }
-                wait_war();
-                store_act(a);
                 signal_act();
             }
             // ---- output layer ----------------------------------------------------------------------------------------
             tl.stamp(41);
             float ssum = 0.f;
+            // z0 of the next chunk is fetched before its accumulators are awaited: the loads do not depend on the conditioner
+            constexpr int ZP = HW > 128 ? 8 : 32;  // prefetched z0 values per thread and chunk (beyond that: loaded in place)
+            float zpre[ZP];
+            auto prefetch_z0 = [&](int q) {
+                const int PC = NW / 2, m0 = q * PC;
+                const int i0 = (CS == 2) ? grp * (PC / 2) : 0, n = PC / CS;
+                const float* zo = zdst + static_cast<size_t>(b) * g.D;
+#pragma unroll
+                for (int k = 0; k < ZP; ++k) {
+                    const int m = m0 + i0 + k;
+                    zpre[k] = (valid && k < n && m < g.c0)
+                                  ? zo[half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx)] : 0.f;
+                }
+            };
+            if (FUSED) prefetch_z0(0);
 #pragma unroll 1
             for (int q = 0; q < nq; ++q) {
                 wait_acc();
@@ -699,7 +781,31 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     const int PC = NW / 2, m0 = q * PC;
                     const int i0 = (CS == 2) ? grp * (PC / 2) : 0, i1 = i0 + PC / CS;
                     float* zo = zdst + static_cast<size_t>(b) * g.D;
-                    for (int i = i0; i < i1; i += 4) {
+#pragma unroll
+                    for (int k4 = 0; k4 < ZP / 4; ++k4) {
+                        const int i = i0 + 4 * k4;
+                        if (i < i1) {
+                            float tm[4], sm[4], tcp[4], scp[4];
+                            tmem_ld<4>(t_lane + static_cast<uint32_t>(i), tm);
+                            tmem_ld<4>(t_lane + static_cast<uint32_t>(PC + i), sm);
+                            tmem_ld<4>(t_lane + static_cast<uint32_t>(NW + i), tcp);
+                            tmem_ld<4>(t_lane + static_cast<uint32_t>(NW + PC + i), scp);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int m = m0 + i + r;
+                                if (valid && m < g.c0) {
+                                    const float t = (tm[r] + tcp[r]) + ob[i + r];
+                                    const float sraw = (sm[r] + scp[r]) + ob[PC + i + r];
+                                    const int off = half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx);
+                                    // coupling.py:107-109: two rounded ops each, no FMA contraction (as in coupling_affine.cu)
+                                    const float s = __fadd_rn(__fmul_rn(tanhf(sraw), sa), sb);
+                                    zo[off] = __fadd_rn(__fmul_rn(zpre[4 * k4 + r], expf(s)), t);
+                                    ssum += s;
+                                }
+                            }
+                        }
+                    }
+                    for (int i = i0 + ZP; i < i1; i += 4) {  // more than ZP channels per thread (c0 > 64 at 16x16 only)
                         float tm[4], sm[4], tcp[4], scp[4];
                         tmem_ld<4>(t_lane + static_cast<uint32_t>(i), tm);
                         tmem_ld<4>(t_lane + static_cast<uint32_t>(PC + i), sm);
@@ -712,13 +818,13 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                                 const float t = (tm[r] + tcp[r]) + ob[i + r];
                                 const float sraw = (sm[r] + scp[r]) + ob[PC + i + r];
                                 const int off = half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx);
-                                // coupling.py:107-109: two rounded ops each, no FMA contraction (as in coupling_affine.cu)
                                 const float s = __fadd_rn(__fmul_rn(tanhf(sraw), sa), sb);
                                 zo[off] = __fadd_rn(__fmul_rn(zo[off], expf(s)), t);
                                 ssum += s;
                             }
                         }
                     }
+                    if (q + 1 < nq) prefetch_z0(q + 1);
                 } else {
                     const int i0 = (CS == 2) ? grp * (NW / 2) : 0, i1 = i0 + NW / CS;
                     for (int i = i0; i < i1; i += 8) {
@@ -749,12 +855,17 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     const int bb = unit * SPU + tid;
                     if (bb < B) {
                         float tot = 0.f;
-                        if (HW == 16) tot = red[(tid >> 1) * 2 + (tid & 1)] + red[((tid >> 1) + 4) * 2 + (tid & 1)];
-                        else if (HW == 64) tot = (red[(2 * tid) * 2] + red[(2 * tid + 1) * 2]) + (red[(2 * tid + 4) * 2] + red[(2 * tid + 5) * 2]);
-                        else {
+                        if (HW > 128) {
 #pragma unroll
                             for (int w8 = 0; w8 < 8; ++w8) tot += red[w8 * 2];
-                        }
+                        } else if (LINKED) {  // paired tiles: warps 4*tile .. 4*tile+3 hold tile `tile`, all 32 channels
+                            const int tl_ = tid / SPT, si = tid % SPT;
+                            if (HW == 16) tot = red[(tl_ * 4 + (si >> 1)) * 2 + (si & 1)];
+                            else if (HW == 64) tot = red[(tl_ * 4 + 2 * si) * 2] + red[(tl_ * 4 + 2 * si + 1) * 2];
+                            else tot = (red[(tl_ * 4) * 2] + red[(tl_ * 4 + 1) * 2]) + (red[(tl_ * 4 + 2) * 2] + red[(tl_ * 4 + 3) * 2]);
+                        } else if (HW == 16) tot = red[(tid >> 1) * 2 + (tid & 1)] + red[((tid >> 1) + 4) * 2 + (tid & 1)];
+                        else if (HW == 64) tot = (red[(2 * tid) * 2] + red[(2 * tid + 1) * 2]) + (red[(2 * tid + 4) * 2] + red[(2 * tid + 5) * 2]);
+                        else tot = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
                         ldj[bb] = __fadd_rn(ldj[bb], tot);  // coupling.py:110
                     }
                 }
@@ -766,6 +877,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     }
 
     __syncthreads();
+    tl_k.stamp(50);
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
@@ -858,10 +970,10 @@ int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout
 // =====================================================================================================================
 // launch
 // =====================================================================================================================
-template <int H, int W, int MODE, bool FUSED>
+template <int H, int W, int MODE, bool FUSED, bool PAIR>
 static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
                      const float* sa, const float* sb, int flags, cudaStream_t st) {
-    using GM = TcGeom<H, W>;
+    using GM = TcGeom<H, W, PAIR>;
     const int dbg = (flags >> NFB_CONV_DEBUG_SHIFT) & 0xff;
     const int gq = (flags >> NFB_CONV_GROUPS_SHIFT) & 7;
     const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer
@@ -869,7 +981,7 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16;
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
-    auto kern = convnet_tc_kernel<H, W, MODE, FUSED>;
+    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int n_units = (B + GM::SPU - 1) / GM::SPU;
     const int grid = n_units < kSMs ? n_units : kSMs;
@@ -880,9 +992,19 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk
 template <int MODE, bool FUSED>
 static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
                       int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
-    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
-    if (h == 8 && w == 8) return launch_tc<8, 8, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
-    if (h == 4 && w == 4) return launch_tc<4, 4, MODE, FUSED>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    // maps of <= 128 pixels: two tiles per CTA when asked for (NFB_CONV_PAIR: several batches in flight) or when the batch
+    // alone gives every SM at least two single-tile units
+    const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;
+    const bool pair = (flags & NFB_CONV_PAIR) ? tiles >= 2 : tiles >= 2 * kSMs;
+    if (h == 8 && w == 8) {
+        if (pair) return launch_tc<8, 8, MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        return launch_tc<8, 8, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    }
+    if (h == 4 && w == 4) {
+        if (pair) return launch_tc<4, 4, MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        return launch_tc<4, 4, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    }
     return NFB_ERR_UNSUPPORTED;
 }
 

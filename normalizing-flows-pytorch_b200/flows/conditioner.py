@@ -16,9 +16,6 @@ import torch.nn.functional as F
 from .. import _lib as L
 from .weight_norm import WeightNorm
 
-# The bits/dim parity bar (1e-5 relative, reference noise floor 2e-7) rules out TF32.
-torch.backends.cudnn.allow_tf32 = False
-torch.backends.cuda.matmul.allow_tf32 = False
 
 
 class _ResBlock(nn.Module):
@@ -73,7 +70,7 @@ class _ResNetConditioner(nn.Module):
         if getattr(self, '_ts', None) is None:
             self._ts = self._tensors()
         ts, wn_eps, bn_eps = self._ts
-        key = tuple([t._version for t in ts])  # in-place updates (optimizer, load_state_dict) bump _version
+        key = L.param_key(ts)  # in-place updates bump _version; graph-replayed optimizer steps bump the global epoch
         if key != getattr(self, '_pack_key', None):
             if len(self.mid_block) != 2 or self.base_filters != 32:
                 raise NotImplementedError('fused conditioner kernel is built for base_filters=32, n_blocks=2 '
@@ -221,6 +218,14 @@ class _ResNetConditioner(nn.Module):
             x = x + y
         x = F.relu(self.out_block[0](x))
         return self._wn_apply(self.out_block[2], x)
+
+
+def set_throughput_mode(on=True):
+    """Default kernel selection of every ConvNet conditioner that has no `kernel_flags` of its own.  on: several batches are
+    in flight (streams, one CUDA graph per stream): 8x8 / 4x4 maps run two tiles per CTA (NFB_CONV_PAIR), which does ~1.5x
+    the work per SM-second on half as many SMs.  off (default): one tile per CTA, the lowest latency of a single batch.
+    Captured CUDA graphs keep the choice they were captured with."""
+    _ResNetConditioner.kernel_flags = L.CONV_PAIR if on else 0
 
 
 class MLP(_ResNetConditioner):

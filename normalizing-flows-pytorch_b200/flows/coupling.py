@@ -168,14 +168,18 @@ class MixLogAttnCoupling(AbstractCoupling):
         self._flag = None
 
     # -- fused conditioner kernel (image case): packed 3x3 weights cached until a parameter changes ------------------
-    def _fpp_tensors(self):
+    def _fpp_params(self):
         n = self.net
-        if getattr(self, '_fpp_ts', None) is None:
-            self._fpp_ts = [n[0].weight, n[0].bias, n[1].op.weight, n[1].op.bias, n[2].weight, n[2].bias, n[3].pos_emb,
-                            n[3].conv1.weight, n[3].conv1.bias, n[3].conv2.weight, n[3].conv2.bias, n[4].weight, n[4].bias,
-                            n[5].weight, n[5].bias]
-        ts = self._fpp_ts
-        key = tuple([t._version for t in ts])
+        return [n[0].weight, n[0].bias, n[1].op.weight, n[1].op.bias, n[2].weight, n[2].bias, n[3].pos_emb,
+                n[3].conv1.weight, n[3].conv1.bias, n[3].conv2.weight, n[3].conv2.bias, n[4].weight, n[4].bias,
+                n[5].weight, n[5].bias]
+
+    def _fpp_tensors(self):
+        """Host array of the 15 device pointers nfb_flowpp_cond_fwd takes (3x3 weights packed, cached until a parameter
+        changes).  Only plain Python objects are stored on the module (deepcopy / pickle safe); the ctypes array is built
+        per call."""
+        ts = self._fpp_params()
+        key = L.param_key(ts)
         if key != getattr(self, '_fpp_key', None):
             packed = {}
             for i in (0, 2, 13):
@@ -185,24 +189,17 @@ class MixLogAttnCoupling(AbstractCoupling):
                 L.check(L.lib().nfb_pack_conv3x3(L.ptr(w), L.ptr(buf), O, I, L.stream()))
                 packed[i] = buf
             self._fpp_packed = packed
-            ptrs = [L.ptr(packed[i]) if i in packed else L.ptr(L.dev(t.data, 'conditioner parameter'))
-                    for i, t in enumerate(ts)]
-            self._fpp_arr = (ctypes.c_void_p * 15)(*ptrs)
+            self._fpp_ptrs = tuple(L.ptr(packed[i]) if i in packed else L.ptr(L.dev(t.data, 'conditioner parameter'))
+                                   for i, t in enumerate(ts))
             self._fpp_key = key
-        return self._fpp_arr
+        return (ctypes.c_void_p * 15)(*self._fpp_ptrs)
 
     def _fpp_tensors_1d(self):
-        """Host array of the 15 raw parameter pointers (nothing is packed for the 1-D kernel); rebuilt after .to()."""
-        if getattr(self, '_fpp_arr1d', None) is None:
-            n = self.net
-            ts = [n[0].weight, n[0].bias, n[1].op.weight, n[1].op.bias, n[2].weight, n[2].bias, n[3].pos_emb,
-                  n[3].conv1.weight, n[3].conv1.bias, n[3].conv2.weight, n[3].conv2.bias, n[4].weight, n[4].bias,
-                  n[5].weight, n[5].bias]
-            self._fpp_arr1d = (ctypes.c_void_p * 15)(*[L.ptr(L.dev(t.data, 'conditioner parameter')) for t in ts])
-        return self._fpp_arr1d
+        """Host array of the 15 raw parameter pointers (nothing is packed for the 1-D kernel), read per call."""
+        return (ctypes.c_void_p * 15)(*[L.ptr(L.dev(t.data, 'conditioner parameter')) for t in self._fpp_params()])
 
     def _apply(self, fn, *a, **k):
-        self._fpp_ts = self._fpp_key = self._fpp_arr1d = None
+        self._fpp_key = None
         return super()._apply(fn, *a, **k)
 
     def _params(self, z):

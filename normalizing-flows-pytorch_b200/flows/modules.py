@@ -14,6 +14,19 @@ from .. import _lib as L
 from . import autograd as G
 
 
+def _world():
+    """Number of ranks of the default process group (1 without one)."""
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+# Cross-sample statistics (ActNorm's data-dependent init, the flow BatchNorm's train-mode batch statistics) are taken over
+# the GLOBAL batch when a process group is initialised: every rank holds a shard, the per-channel moments are all-reduced
+# (parallel.actnorm_init_sharded / batchnorm_stats_sharded), and all replicas end up with identical values -- as if the
+# reference had seen the whole batch on one device.  Set to False for rank-local statistics.
+SYNC_STATS = True
+
+
 def _bchw(z):
     if z.dim() == 2:
         return z.size(0), z.size(1), 1
@@ -66,8 +79,12 @@ class ActNorm(nn.Module):
         z, log_df_dz = L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz')
         B, C, HW = _bchw(z)
         if not self.initialized:
-            L.check(L.lib().nfb_actnorm_init(L.ptr(z), L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW,
-                                             float(self.eps), L.stream()))
+            if SYNC_STATS and _world() > 1:
+                from ..parallel import actnorm_init_sharded
+                actnorm_init_sharded(self, z)  # moments of the global batch (one all-reduce of 2C+1 doubles)
+            else:
+                L.check(L.lib().nfb_actnorm_init(L.ptr(z), L.ptr(self.log_scale.data), L.ptr(self.bias.data), B, C, HW,
+                                                 float(self.eps), L.stream()))
             self.initialized = True
         if G.needs_grad(z, log_df_dz, self.log_scale, self.bias):
             return G.ActNormFn.apply(z, log_df_dz, self.log_scale, self.bias)
@@ -116,7 +133,10 @@ class BatchNorm(nn.Module):
     def forward(self, x, log_det_jacob):
         x, log_det_jacob = L.dev(x, 'x'), L.dev(log_det_jacob, 'log_det_jacob')
         B, C, HW = _bchw(x)
-        if self.training:
+        if self.training and SYNC_STATS and _world() > 1:
+            from ..parallel import batchnorm_stats_sharded
+            batchnorm_stats_sharded(self, x)  # batch statistics of the global batch + running-statistic update
+        elif self.training:
             L.check(L.lib().nfb_bnflow_batch_stats(L.ptr(x), L.ptr(self.batch_mean), L.ptr(self.batch_var), B, C, HW,
                                                    float(self.eps), L.stream()))
             with torch.no_grad():  # modules.py:291-294 (C-element bookkeeping)
@@ -172,7 +192,7 @@ class InvertibleConv1x1(nn.Module):
     def matrices(self):
         """(W, W^-1) device tensors, rebuilt only when a parameter changed."""
         ps = (self.P, self.L, self.U, self.log_s, self.sign_s)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = L.param_key(ps)
         if key != self._cache_key:
             C = self.L.size(0)
             dev = self.L.device

@@ -33,7 +33,7 @@ class WeightNorm(nn.Module):
     def weight(self):
         """Folded weight w = v * g / (||v|| + eps) as a device tensor shaped like v."""
         g, v = self.module.weight_g, self.module.weight_v
-        key = (g.data_ptr(), g._version, v.data_ptr(), v._version)
+        key = L.param_key((g, v))
         if key != self._key:
             L.dev(v.data, 'weight_v')
             if self._w is None or self._w.device != v.device:

@@ -7,6 +7,7 @@ batch with replicated weights; there is NO data-path collective.  The only excha
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from .likelihood import LN2
 
 
@@ -120,8 +121,11 @@ def train_step(model, optimizer, x_local, group=None):
     """One optimisation step of main.py:78-92 on this rank's shard of the global batch.
 
     loss = mean over the GLOBAL batch of -(log N(z; 0, I) + ldj): every rank back-propagates sum(local NLL) / B_global
-    and the gradients are summed across ranks, so the update equals the single-process step on the whole batch whatever
-    the shard sizes.  (Train-mode BatchNorm statistics inside the conditioners stay per-rank, as in plain DDP.)
+    and the gradients are summed across ranks.  Cross-sample state: ActNorm's first-call init and the flow BatchNorm's
+    train-mode statistics use the all-reduced moments of the global batch (flows.modules.SYNC_STATS), so the replicas
+    hold identical bijection parameters and buffers; the nn.BatchNorm layers INSIDE the conditioners keep per-rank batch
+    statistics, as in plain DDP -- with them the update equals the single-process step up to that difference (exactly for
+    stacks whose conditioners run in eval mode).
     Returns the global mean NLL as a float."""
     rows, total = model.nll(x_local)
     total = allreduce_nll(total.clone(), group)
@@ -165,8 +169,11 @@ class GraphedTrainStep:
         self.count = torch.ones((), device=example.device, dtype=torch.float32)   # global batch size, device-resident
         self.loss = torch.zeros((), device=example.device, dtype=torch.float32)
         self._sync_count()
+        was_training = model.training
         with torch.no_grad():
+            model.eval()   # eval: no BatchNorm running-statistic update from this forward
             model(self.x)  # ActNorm's data-dependent init (modules.py:238-244) happens here if it has not yet
+            model.train(was_training)
         # warm-up steps (allocator, cuDNN plans, optimizer state) must not move the model: snapshot, restore below
         snap = {k: v.clone() for k, v in model.state_dict().items()}
         side = torch.cuda.Stream()
@@ -217,4 +224,7 @@ class GraphedTrainStep:
         self.g_fb.replay()
         self._reduce()
         self.g_opt.replay()
+        # the replayed optimizer step rewrote the parameters without bumping their _version counters: every derived-weight
+        # cache (folded conditioner weights, W / W^-1, WeightNorm folds) must be rebuilt by the next eval forward
+        L.bump_weights_epoch()
         return self.loss

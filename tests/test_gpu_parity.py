@@ -509,6 +509,17 @@ def test_fused_conditioner_coupling(dims, masking, odd, B):
     _, z1_in = m.coupling_split(x, cpl.mode, cpl.odd, want_z0=False)
     _, z1_out = m.coupling_split(z1, cpl.mode, cpl.odd, want_z0=False)
     assert torch.equal(z1_in, z1_out)
+    # two tiles per CTA (throughput mode): the second tile of a pair issues its taps in another order (other rounding of the
+    # same sums), so equality is to rounding, and the fused / two-kernel paths of THIS mode are again bit-identical
+    cpl.fused_conditioner = True
+    cpl.net.kernel_flags = L.CONV_PAIR
+    z4, l4 = cpl(x, l0.clone())
+    sc = max(1.0, float(z1.abs().max()))
+    close(z4, z1, rtol=2e-6, atol=1e-6 * sc, what='paired tiles vs single tile')
+    close(l4, l1, rtol=2e-6, atol=1e-4, what='ldj (paired tiles)')
+    cpl.fused_conditioner = False
+    z5, _ = cpl(x, l0.clone())
+    assert torch.equal(z4, z5)
     cpl.net.kernel_flags = L.CONV_FFMA
     z3, l3 = cpl(x, l0.clone())
     scale = max(1.0, float(z3.abs().max()))
