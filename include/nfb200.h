@@ -82,6 +82,16 @@ int nfb_mixlog_coupling_inv(const float* z_in, float* z_out, const float* params
                             int* stall_flag, int B, int C, int H, int W, int mode, int odd, int K,
                             nfb_stream_t stream);
 
+/* MixLogCDF.forward (modules.py:190-194) as a standalone layer, with mix_logistic_logpdf / mix_logistic_logcdf and the
+ * logistic_* helpers (modules.py:64-97) inside: x (B, n), log_pi / mu / s (B, K, n) as given (no normalisation);
+ * y = exp(mix_logcdf(x)), ldj_out[b] = ldj_in[b] + sum_n mix_logpdf(x). */
+int nfb_mixlogcdf_fwd(const float* x, float* y, const float* log_pi, const float* mu, const float* s,
+                      const float* ldj_in, float* ldj_out, int B, int n, int K, nfb_stream_t stream);
+/* MixLogCDF.backward (modules.py:196-212): bisection on [-1e3, 1e3], the reference's global 25 / 100 iteration rule as in
+ * nfb_mixlog_coupling_inv (scratch: 2*B*n floats, stall_flag: device int); ldj_out[b] = ldj_in[b] - sum_n mix_logpdf(x). */
+int nfb_mixlogcdf_inv(const float* y, float* x, const float* log_pi, const float* mu, const float* s, const float* ldj_in,
+                      float* ldj_out, float* scratch, int* stall_flag, int B, int n, int K, nfb_stream_t stream);
+
 /* Rational-quadratic spline coupling (Durkan et al. 2019; no counterpart in the reference -- parity unpinned):
  * params = (B, (3K-1)*c0, h, w), sections [widths(K) | heights(K) | derivatives(K-1)], bin channel = k*c0 + m;
  * identity outside [-bound, bound], boundary derivatives 1. */

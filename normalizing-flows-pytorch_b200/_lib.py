@@ -44,6 +44,8 @@ _SIGNATURES = {
     'nfb_additive_coupling': [_P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P],
     'nfb_mixlog_coupling_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_mixlog_coupling_inv': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'nfb_mixlogcdf_fwd': [_P] * 7 + [_I] * 3 + [_P],
+    'nfb_mixlogcdf_inv': [_P] * 9 + [_I] * 3 + [_P],
     'nfb_rqs_coupling_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'nfb_rqs_coupling_inv': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'nfb_coupling_split': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -62,6 +62,45 @@ class Logit(nn.Module):
     inverse = backward
 
 
+class MixLogCDF(nn.Module):
+    """modules.py:186-212: the logistic-mixture CDF as a bijection of x given (log_pi, mu, s) of shape (B, K, *x.shape[1:]);
+    `backward` is the reference's bisection.  Returns NEW log-det tensors like the reference.  (MixLogAttnCoupling runs the
+    same arithmetic fused with its logit / affine stages, coupling.py:183-189.)"""
+
+    def __init__(self):
+        super().__init__()
+        self._scratch = self._flag = None
+
+    @staticmethod
+    def _args(x, log_pi, mu, s, log_df_dz):
+        x, log_df_dz = L.dev(x, 'x'), L.dev(log_df_dz, 'log_df_dz')
+        log_pi, mu, s = L.dev(log_pi, 'log_pi'), L.dev(mu, 'mu'), L.dev(s, 's')
+        B, K = log_pi.size(0), log_pi.size(1)
+        n = x[0].numel()
+        if not (log_pi.shape == mu.shape == s.shape) or log_pi[0, 0].numel() != n or x.size(0) != B:
+            raise RuntimeError('nfb200: MixLogCDF expects x (B, ...) and log_pi / mu / s (B, K, ...) of matching shapes')
+        return x, log_pi, mu, s, log_df_dz, B, n, K
+
+    def forward(self, x, log_pi, mu, s, log_df_dz):
+        x, log_pi, mu, s, log_df_dz, B, n, K = self._args(x, log_pi, mu, s, log_df_dz)
+        y, ldj = torch.empty_like(x), torch.empty_like(log_df_dz)
+        L.check(L.lib().nfb_mixlogcdf_fwd(L.ptr(x), L.ptr(y), L.ptr(log_pi), L.ptr(mu), L.ptr(s), L.ptr(log_df_dz),
+                                          L.ptr(ldj), B, n, K, L.stream()))
+        return y, ldj
+
+    def backward(self, x, log_pi, mu, s, log_df_dz):
+        x, log_pi, mu, s, log_df_dz, B, n, K = self._args(x, log_pi, mu, s, log_df_dz)
+        if self._scratch is None or self._scratch.numel() < 2 * B * n or self._scratch.device != x.device:
+            self._scratch = torch.empty(2 * B * n, device=x.device, dtype=torch.float32)
+            self._flag = torch.zeros(1, device=x.device, dtype=torch.int32)
+        out, ldj = torch.empty_like(x), torch.empty_like(log_df_dz)
+        L.check(L.lib().nfb_mixlogcdf_inv(L.ptr(x), L.ptr(out), L.ptr(log_pi), L.ptr(mu), L.ptr(s), L.ptr(log_df_dz),
+                                          L.ptr(ldj), L.ptr(self._scratch), L.ptr(self._flag), B, n, K, L.stream()))
+        return out, ldj
+
+    inverse = backward
+
+
 class ActNorm(nn.Module):
     """modules.py:225-256 (data-dependent init on the first call; ``initialized`` is a plain attribute)."""
 

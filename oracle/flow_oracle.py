@@ -357,6 +357,22 @@ def affine_transform(z0, params, ldj, s_log_scale, s_bias, inverse=False):
     return torch.exp(-s) * (z0 - t), ldj - _rowsum(s)
 
 
+def additive_transform(z0, t, ldj, inverse=False):
+    """AdditiveCoupling._transform / _inverse_transform (coupling.py:69-79): z0 +- net_t(z1); no log-det."""
+    return (z0 - t if inverse else z0 + t), ldj
+
+
+def mixlogcdf_fwd(x, log_pi, mu, s, ldj):
+    """MixLogCDF.forward (modules.py:190-194); log_pi / mu / s are (B, K, *x.shape[1:])."""
+    return torch.exp(mixlog_logcdf(x, log_pi, mu, s)), ldj + _rowsum(mixlog_logpdf(x, log_pi, mu, s))
+
+
+def mixlogcdf_inv(y, log_pi, mu, s, ldj):
+    """MixLogCDF.backward (modules.py:196-212): bisection, then ldj - sum log-pdf at the root."""
+    x, _ = mixlog_bisect(y, log_pi, mu, s)
+    return x, ldj - _rowsum(mixlog_logpdf(x, log_pi, mu, s))
+
+
 def _mix_params(z0, params, K, a_log_scale, a_bias):
     B, c0 = z0.shape[:2]
     tail = z0.shape[2:]
@@ -531,6 +547,8 @@ def _coupling(kind, opt, sd, p, z, ldj, inverse, train=False):
         params = flowpp_conditioner(sd, p + 'net.', z1)
         f = mixlog_inverse if inverse else mixlog_transform
         z0, ldj = f(z0, params, ldj, opt['mixtures'], sd[p + 'a_log_scale'], sd[p + 'a_bias'])
+    elif kind == 'additive':
+        z0, ldj = additive_transform(z0, resnet_conditioner(sd, p + 'net_t.', z1, train), ldj, inverse)
     else:
         params = resnet_conditioner(sd, p + 'net.', z1, train)
         if kind == 'affine':

@@ -76,6 +76,20 @@ def run_layer(layer, x, ldj0):
                 inv_ldj=l2.numpy())
 
 
+def gen_layer_case(gen, name, ctor, ctor_kwargs, x, pre=None):
+    """One layer: seeded construction, perturbed parameters, forward + backward through the reference, saved as <name>.npz."""
+    torch.manual_seed(7)
+    layer = ctor(**ctor_kwargs)
+    perturb(layer, gen)
+    if pre is not None:
+        pre(layer)
+    ldj0 = torch.randn(x.shape[0], generator=gen)
+    arrays = run_layer(layer, x, ldj0)
+    arrays.update(sd_np(layer))
+    kw = {k: (list(v) if isinstance(v, tuple) else v) for k, v in ctor_kwargs.items()}
+    save(name, dict(kind=ctor.__name__, kwargs=kw), arrays)
+
+
 def main():
     gen = torch.Generator().manual_seed(1234)
 

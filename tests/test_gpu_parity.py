@@ -100,7 +100,23 @@ def build_layer(meta):
     return layer
 
 
-LAYER_CASES = [n for n in _golden.names() if not n.startswith(('model_', 'permutations', 'stats_', 'grad_'))]
+LAYER_CASES = [n for n in _golden.names() if not n.startswith(('model_', 'permutations', 'stats_', 'grad_', 'mixlogcdf_'))]
+
+
+@pytest.mark.parametrize('name', _golden.names('mixlogcdf_'))
+def test_mixlogcdf_module_vs_reference_golden(name):
+    """nfb200.flows.MixLogCDF (standalone module of modules.py:186-212) against the reference's outputs."""
+    F = nfb().flows
+    _, a, _ = _golden.load(name)
+    m = F.MixLogCDF()
+    d = {k: v.to(DEV) for k, v in a.items()}
+    y, l1 = m(d['x'], d['log_pi'], d['mu'], d['s'], d['ldj0'].clone())
+    close(y, a['fwd_y'], what=name + ' fwd y')
+    close(l1, a['fwd_ldj'], rtol=1e-5, atol=2e-5, what=name + ' fwd ldj')
+    x, l2 = m.backward(d['fwd_y'], d['log_pi'], d['mu'], d['s'], d['ldj0'].clone())
+    close(x, a['inv_x'], rtol=2e-4, atol=2e-4, what=name + ' inv x')  # the reference's bisection bracket is 1e-4 wide
+    close(l2, a['inv_ldj'], rtol=2e-4, atol=4e-3, what=name + ' inv ldj')
+    assert torch.equal(d['ldj0'], a['ldj0'].to(DEV))  # returns NEW log-det tensors (modules.py:194)
 
 
 @pytest.mark.parametrize('name', LAYER_CASES)
@@ -175,6 +191,97 @@ def test_model_vs_reference_golden(name):
 
 def oracle_spec(model, dims, datatype, layers, mixtures=4, coupling=None):
     return O.stack_spec(model, dims, datatype, layers, mixtures, coupling)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(model='glow', dims=(3, 32, 32), datatype='image', layers=32, B=256),                      # BASELINE configs[1]
+    dict(model='flowpp', dims=(3, 32, 32), datatype='image', layers=32, mixtures=8, B=32),         # configs[2] (CPU-bounded B)
+    dict(model='realnvp', dims=(64, ), datatype=None, layers=8, coupling='rqs', B=65536),           # configs[3]
+    dict(model='glow', dims=(3, 64, 64), datatype='image', layers=48, B=8),                        # configs[4] (CPU-bounded B)
+    dict(model='realnvp', dims=(2, ), datatype=None, layers=6, B=512),                              # configs[0]
+], ids=['glow32_K32_B256', 'flowpp32_K32_M8_B32', 'realnvp64_rqs_B65536', 'glow64_K48_B8', 'realnvp2_B512'])
+def test_full_depth_config_bits_per_dim(cfg):
+    """The BASELINE.json configurations at FULL depth: bits/dim of the GPU path within 1e-5 (relative) of the CPU oracle on
+    the same weights and inputs -- the north-star parity bar, here inside pytest and not only in bench.py."""
+    n = nfb()
+    torch.manual_seed(0)
+    cls = {'glow': n.Glow, 'realnvp': n.RealNVP, 'flowpp': n.Flowpp}[cfg['model']]
+    extra = {'coupling': cfg['coupling']} if cfg.get('coupling') else {}
+    net = cls(cfg['dims'], cfg['datatype'], types.SimpleNamespace(layers=cfg['layers'], mixtures=cfg.get('mixtures', 4), **extra))
+    net.eval()
+    g = torch.Generator().manual_seed(0)
+    shape = (cfg['B'], ) + tuple(cfg['dims'])
+    x = torch.rand(shape, generator=g) if cfg['datatype'] == 'image' else torch.randn(shape, generator=g)
+    net.to(DEV)
+    net(x.to(DEV))  # ActNorm data-dependent init on the device (modules.py:238-244); the oracle gets the resulting state
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    bpd_gpu = net.bits_per_dim(x.to(DEV))
+    spec = O.stack_spec(cfg['model'], cfg['dims'], cfg['datatype'], cfg['layers'], cfg.get('mixtures', 4), cfg.get('coupling'))
+    torch.set_num_threads(max(1, (__import__('os').cpu_count() or 1)))
+    z, ldj = O.stack_forward(spec, sd, x)
+    bpd_cpu = O.bits_per_dim(z, ldj)
+    rel = abs(bpd_gpu - bpd_cpu) / abs(bpd_cpu)
+    print('%s: bits/dim gpu %.9f cpu %.9f rel %.2e' % (cfg['model'], bpd_gpu, bpd_cpu, rel))
+    assert rel <= 1e-5, (bpd_gpu, bpd_cpu, rel)
+
+
+def test_no_library_fallbacks_on_baseline_configs():
+    """Eval-mode forwards of the five BASELINE stacks stay on libnfb200 kernels: the library-path counter does not move."""
+    n = nfb()
+    n0 = n.library_path_calls()
+    for model, dims, dt, layers, extra, B in (('Glow', (3, 32, 32), 'image', 2, {}, 4), ('Flowpp', (3, 32, 32), 'image', 1, {}, 2),
+                                              ('RealNVP', (64, ), None, 2, {'coupling': 'rqs'}, 64),
+                                              ('Glow', (3, 64, 64), 'image', 1, {}, 2), ('RealNVP', (2, ), None, 2, {}, 32)):
+        torch.manual_seed(0)
+        net = getattr(n, model)(dims, dt, types.SimpleNamespace(layers=layers, mixtures=8, **extra)).to(DEV).eval()
+        x = torch.rand((B, ) + dims, device=DEV) if dt == 'image' else torch.randn((B, ) + dims, device=DEV)
+        net(x)
+        net(x)
+    assert n.library_path_calls() == n0, n.library_path_log()
+
+
+def test_reference_stack_rebound_to_nfb200_layers():
+    """INTEGRATION.md section 1 executed on the device: the REFERENCE's own Glow builder (glow.py:17-60) with its layer
+    classes rebound to nfb200's (glow.py:27-29,37-39,43-45), a reference state dict loaded strictly, forward on the GPU --
+    against the output the unmodified reference produced on the CPU (tests/golden/model_glow_16.npz)."""
+    import importlib
+    import os
+    import sys
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'flows')):
+        pytest.skip('oracle/_ref (the staged reference package) is not present')
+    n = nfb()
+    nf = n.flows
+    sys.path.insert(0, ref_dir)
+    try:
+        import flows.glow as rglow
+        importlib.reload(rglow)
+        saved = {}
+        for name in ('Logit', 'ActNorm', 'BatchNorm', 'InvertibleConv1x1', 'Compose', 'AffineCoupling', 'AdditiveCoupling',
+                     'MixLogAttnCoupling', 'Squeeze2d', 'Unsqueeze2d'):
+            if hasattr(rglow, name):
+                saved[name] = getattr(rglow, name)
+                setattr(rglow, name, getattr(nf, name))
+        try:
+            meta, a, sd = _golden.load('model_glow_16')
+            cfg = types.SimpleNamespace(layers=meta['layers'], mixtures=meta['mixtures'])
+            net = rglow.Glow(dims=tuple(meta['dims']), datatype=meta['datatype'], cfg=cfg)  # the reference's constructor
+            assert type(net.net) is nf.Compose and any(type(m) is nf.AffineCoupling for m in net.modules())
+            net.load_state_dict(sd, strict=True)
+            for m in net.modules():
+                if isinstance(m, nf.ActNorm):
+                    m.initialized = True
+            net.to(DEV).eval()
+            z, ldj = net(a['x'].to(DEV))  # Glow.forward of the reference (glow.py:62-64) over nfb200 layers
+            close(z, a['fwd_z'], rtol=5e-5, atol=5e-5, what='rebound glow z')
+            close(ldj, a['fwd_ldj'], rtol=1e-5, atol=2e-4, what='rebound glow ldj')
+            y, ldj2 = net.backward(a['fwd_z'].to(DEV))
+            close(y, a['inv_y'], rtol=2e-4, atol=2e-4, what='rebound glow inverse')
+        finally:
+            for name, cls in saved.items():
+                setattr(rglow, name, cls)
+    finally:
+        sys.path.remove(ref_dir)
 
 
 def perturb_(net, seed=0):
