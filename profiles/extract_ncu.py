@@ -42,6 +42,9 @@ def main():
             return f * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'us': 1, 'ns': 1e-3, 'ms': 1e3}.get(u, 1)
         summary = {'kernel': d['Kernel Name'][0], 'dram_bytes_per_launch': num('dram__bytes_read.sum') + num('dram__bytes_write.sum'),
                    'time_us_under_ncu': num('gpu__time_duration.sum'), 'registers': d['launch__registers_per_thread'][0]}
+        tp = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'
+        if tp in d:
+            summary['tensor_pipe_active_pct'] = float(d[tp][0].replace(',', ''))
     with open(out, 'w') as f:
         f.write('\n'.join(lines) + '\n')
     if key:
