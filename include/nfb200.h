@@ -235,6 +235,17 @@ int nfb_convnet_fwd_ex(const float* src, float* params_out, const float* packed,
  * nfb_convnet_fwd + nfb_affine_coupling_fwd.  flags as for nfb_convnet_fwd_ex. */
 int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale, const float* s_bias,
                            int B, int C, int H, int W, int mode, int odd, int flags, nfb_stream_t stream);
+/* nfb_convnet_affine_fwd followed, inside the same kernel, by the NEXT flow step's ActNorm.forward (modules.py:246-250) and
+ * InvertibleConv1x1.forward (modules.py:470-480) on the samples the CTA has just finished: z <- W ((z' - bias) / exp(log_scale)),
+ * ldj += (sum log_s - sum log_scale) * H*W, all in place -- a Glow flow step is then ONE launch (glow.py:27-29: this
+ * step's coupling + the next step's ActNorm and 1x1 conv).  next_W: the matrix from nfb_invconv1x1_weight.  Implemented
+ * where it beats a separate launch -- 16x16 conditioner maps with C = 3 or 12, 8x8 maps with C = 12 (small per-pixel
+ * matrices); otherwise NFB_ERR_UNSUPPORTED: run nfb_convnet_affine_fwd and nfb_actnorm_invconv_fwd. */
+int nfb_convnet_affine_step_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale, const float* s_bias,
+                                const float* next_log_scale, const float* next_bias, const float* next_W,
+                                const float* next_log_s, int B, int C, int H, int W, int mode, int odd, int flags,
+                                nfb_stream_t stream);
+
 /* Flow++ conditioner (coupling.py:160-167: Conv2d(in,32,3) -> GatedConv2d -> LayerNorm -> GatedAttn(4 heads) ->
  * LayerNorm -> Conv2d(32,out,3); modules.py:519-578) as ONE kernel.  `tensors`: HOST array of 15 device pointers:
  * net.0 weight packed by nfb_pack_conv3x3, net.0.bias, net.1.op weight packed, net.1.op.bias, net.2.weight, net.2.bias,

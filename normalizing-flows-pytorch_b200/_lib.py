@@ -72,6 +72,7 @@ _SIGNATURES = {
     'nfb_convnet_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_convnet_fwd_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_convnet_affine_fwd': [_P] * 5 + [_I] * 7 + [_P],
+    'nfb_convnet_affine_step_fwd': [_P] * 9 + [_I] * 7 + [_P],
     'nfb_pack_conv3x3': [_P, _P, _I, _I, _P],
     'nfb_flowpp_cond_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'nfb_flowpp_mlp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

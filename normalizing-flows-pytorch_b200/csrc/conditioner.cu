@@ -676,6 +676,22 @@ extern "C" int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed,
                                       s_bias, flags, as_stream(stream));
 }
 
+extern "C" int nfb_convnet_affine_step_fwd(float* z, float* ldj, const float* packed, const float* s_log_scale,
+                                           const float* s_bias, const float* next_log_scale, const float* next_bias,
+                                           const float* next_W, const float* next_log_s, int B, int C, int H, int W, int mode,
+                                           int odd, int flags, nfb_stream_t stream) {
+    if (!z || !ldj || !packed || !s_log_scale || !s_bias || !next_log_scale || !next_bias || !next_W || !next_log_s)
+        return NFB_ERR_NULL;
+    SplitGeom g;
+    const int rc = make_geom(g, B, C, H, W, mode, odd);
+    if (rc != NFB_OK) return rc;
+    if (mode != NFB_SPLIT_CHECKER && mode != NFB_SPLIT_CHANNEL) return NFB_ERR_UNSUPPORTED;
+    if (flags & NFB_CONV_FFMA) return NFB_ERR_UNSUPPORTED;
+    return convnet_affine_step_tc_dispatch(z, ldj, packed + tc_plan(g.c0, 2 * g.c0).base, g, mode, g.c0, 2 * g.c0, B,
+                                           s_log_scale, s_bias, next_log_scale, next_bias, next_W, next_log_s, flags,
+                                           as_stream(stream));
+}
+
 extern "C" int nfb_mlp_fwd(const float* src, float* params_out, const float* packed, int B, int C, int mode, int odd,
                            int in_ch, int out_ch, nfb_stream_t stream) {
     if (!src || !params_out || !packed) return NFB_ERR_NULL;

@@ -154,6 +154,9 @@ int convnet_tc_dispatch(const float* zsrc, float* out, const float* pk_tc, const
                         int B, int h, int w, int flags, cudaStream_t st);
 int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout, int B,
                                const float* sa, const float* sb, int flags, cudaStream_t st);
+int convnet_affine_step_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
+                                    int B, const float* sa, const float* sb, const float* an_ls, const float* an_b,
+                                    const float* Wm, const float* log_s, int flags, cudaStream_t st);
 int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace nfb

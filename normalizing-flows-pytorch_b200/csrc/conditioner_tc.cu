@@ -302,7 +302,7 @@ struct TcGeom {
     static constexpr int SPU = HW > 128 ? 1 : T * SPT;  // samples per unit
     static constexpr int CS = LINKED ? 1 : 2;           // epilogue warps per TMEM lane quarter of one tile
     static constexpr int NCH = 32 / CS;                 // channels per epilogue thread
-    static constexpr int GUARD = (W + 1 + 3) & ~3;      // positions before / after the tiles (tap offsets reach there)
+    static constexpr int GUARD = W + 1;                 // positions before / after the tiles (tap offsets reach there)
     static constexpr int PB = 2 * GUARD + T * 128;      // positions per channel-chunk plane
     static constexpr int PS = PB * 16;                  // bytes per plane
     static constexpr int ACT_BYTES = 16 * PS;           // 8 hi planes + 8 lo planes
@@ -316,10 +316,19 @@ struct TcGeom {
 // =====================================================================================================================
 // the kernel
 // =====================================================================================================================
-template <int H, int W, int MODE, bool FUSED, bool PAIR>
+// The NEXT flow step's ActNorm + invertible 1x1 convolution (modules.py:246-250, 470-480), run by the same CTA on the
+// samples it has just finished (CP = channels of z, compile time: the per-pixel matrix-vector product lives in registers).
+struct PostOp {
+    const float* an_log_scale;  // (C)
+    const float* an_bias;       // (C)
+    const float* W;             // (C, C) row-major, from nfb_invconv1x1_weight
+    const float* log_s;         // (C)
+};
+
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP>
 __global__ void __launch_bounds__(kThreads, 1)
 convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
-                  int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, int G, int dbg) {
+                  int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, PostOp post, int G, int dbg) {
     using GM = TcGeom<H, W, PAIR>;
     constexpr int HW = GM::HW, T = GM::T, SPT = GM::SPT, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD,
                   PB = GM::PB, PS = GM::PS;
@@ -338,6 +347,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [8 warps][2]
     uint4* mask_tab = reinterpret_cast<uint4*>(red + 16);        // [T][9 taps]: rows of the tile whose tap leaves the image
     uint4* prog = mask_tab + 2 * 9;                              // [T][9 taps in issue order][mask, 4 k-steps]: see below
+    float* wpost = reinterpret_cast<float*>(prog + 2 * 9 * 5);   // CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
 
@@ -385,6 +395,22 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         if (j == 0)
             prog[(t * 9 + i) * 5] = make_uint4(edge_mask<H, W>(t, dy, dx, 0), edge_mask<H, W>(t, dy, dx, 1),
                                                edge_mask<H, W>(t, dy, dx, 2), edge_mask<H, W>(t, dy, dx, 3));
+    }
+    if (CP > 0) {
+        for (int i = tid; i < CP * CP; i += kThreads) {
+            const int ci = i / CP, co = i - ci * CP;
+            wpost[i] = __ldg(post.W + co * CP + ci);  // transposed Wt[ci][co]: consecutive outputs of one input are contiguous
+        }
+        if (tid < CP) {
+            wpost[CP * CP + tid] = expf(__ldg(post.an_log_scale + tid));
+            wpost[CP * CP + CP + tid] = __ldg(post.an_bias + tid);
+        }
+        if (tid == 0) {
+            float an = 0.f, cv = 0.f;
+            for (int c = 0; c < CP; ++c) { an -= __ldg(post.an_log_scale + c); cv += __ldg(post.log_s + c); }
+            wpost[CP * CP + 2 * CP] = an;
+            wpost[CP * CP + 2 * CP + 1] = cv;
+        }
     }
     {
         const float* src = pk + P.consts;
@@ -866,10 +892,52 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         } else if (HW == 16) tot = red[(tid >> 1) * 2 + (tid & 1)] + red[((tid >> 1) + 4) * 2 + (tid & 1)];
                         else if (HW == 64) tot = (red[(2 * tid) * 2] + red[(2 * tid + 1) * 2]) + (red[(2 * tid + 4) * 2] + red[(2 * tid + 5) * 2]);
                         else tot = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
-                        ldj[bb] = __fadd_rn(ldj[bb], tot);  // coupling.py:110
+                        float l = __fadd_rn(ldj[bb], tot);  // coupling.py:110
+                        if (CP > 0) {
+                            const float hw_full = static_cast<float>(g.HW);
+                            l = __fadd_rn(l, __fmul_rn(wpost[CP * CP + 2 * CP], hw_full));      // ActNorm, modules.py:249
+                            l = __fadd_rn(l, __fmul_rn(wpost[CP * CP + 2 * CP + 1], hw_full));  // 1x1 conv, modules.py:480
+                        }
+                        ldj[bb] = l;
                     }
                 }
+                if (CP > 0) __threadfence_block();  // this CTA's z0 stores are visible to all its threads after the barrier
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (CP > 0) {
+                    // next step's ActNorm + 1x1 conv, in place: thread = pixel; the CP normalised inputs stay in registers, the
+                    // outputs are produced one channel at a time (rolled loop over co, unrolled dot product over ci: the same
+                    // ascending-ci fmaf chain as invconv_apply_tiled) and stored at once -- the originals are no longer needed
+                    const float* es = wpost + CP * CP;
+                    const float* bs = es + CP;
+                    const int npix = SPU * g.HW;
+                    for (int pp = tid; pp < npix; pp += kEpiThreads) {
+                        const int sl = pp / g.HW, px = pp - sl * g.HW;
+                        const int bb = unit * SPU + sl;
+                        if (bb >= B) continue;
+                        float* zp = zdst + static_cast<size_t>(bb) * g.D + px;
+                        float vn[CP > 0 ? CP : 1];
+#pragma unroll
+                        for (int c = 0; c < CP; ++c) vn[c] = zp[static_cast<size_t>(c) * g.HW];
+#pragma unroll
+                        for (int c = 0; c < CP; ++c) vn[c] = __fdiv_rn(__fsub_rn(vn[c], bs[c]), es[c]);  // modules.py:246
+                        // COB output channels at a time: COB independent fmaf chains (each still ascending in ci)
+                        constexpr int COB = CP >= 48 ? 8 : (CP % 4 == 0 ? 4 : (CP > 0 ? CP : 1));
+#pragma unroll 1
+                        for (int co = 0; co < CP; co += COB) {
+                            const float* wr = wpost + co;
+                            float acc[COB];
+#pragma unroll
+                            for (int r = 0; r < COB; ++r) acc[r] = 0.f;
+#pragma unroll
+                            for (int ci = 0; ci < CP; ++ci) {
+#pragma unroll
+                                for (int r = 0; r < COB; ++r) acc[r] = fmaf(wr[ci * CP + r], vn[ci], acc[r]);  // modules.py:477
+                            }
+#pragma unroll
+                            for (int r = 0; r < COB; ++r) zp[static_cast<size_t>(co + r) * g.HW] = acc[r];
+                        }
+                    }
+                }
             }
         }
         tl.stamp(42);
@@ -970,22 +1038,23 @@ int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout
 // =====================================================================================================================
 // launch
 // =====================================================================================================================
-template <int H, int W, int MODE, bool FUSED, bool PAIR>
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP = 0>
 static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
-                     const float* sa, const float* sb, int flags, cudaStream_t st) {
+                     const float* sa, const float* sb, int flags, cudaStream_t st, const PostOp& post = PostOp{}) {
     using GM = TcGeom<H, W, PAIR>;
     const int dbg = (flags >> NFB_CONV_DEBUG_SHIFT) & 0xff;
     const int gq = (flags >> NFB_CONV_GROUPS_SHIFT) & 7;
     const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer
     const TcPlan P = tc_plan(Cin, Cout);
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
-    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16;
+    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16 +
+                        (CP > 0 ? static_cast<size_t>(CP * CP + 2 * CP + 4) * 4 : 0);
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
-    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR>;
+    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int n_units = (B + GM::SPU - 1) / GM::SPU;
     const int grid = n_units < kSMs ? n_units : kSMs;
-    kern<<<grid, kThreads, smem, st>>>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, G, dbg);
+    kern<<<grid, kThreads, smem, st>>>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, post, G, dbg);
     return launch_status();
 }
 
@@ -1005,6 +1074,36 @@ static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* p
         if (pair) return launch_tc<4, 4, MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
         return launch_tc<4, 4, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     }
+    return NFB_ERR_UNSUPPORTED;
+}
+
+// conditioner + coupling + the next step's ActNorm / 1x1 conv: the (map size, channel count) pairs of the Glow stacks
+template <int MODE>
+static int tc_step_by_size(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B, const float* sa,
+                           const float* sb, int flags, cudaStream_t st, const PostOp& post) {
+    const int h = g.h, w = g.w, C = g.C;
+    const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;
+    const bool pair = (flags & NFB_CONV_PAIR) ? tiles >= 2 : tiles >= 2 * kSMs;
+#define NFB_STEP(H_, W_, PAIR_, CP_) return launch_tc<H_, W_, MODE, true, PAIR_, CP_>(z, z, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st, post)
+    if (h == 16 && w == 16) {
+        if (C == 3) NFB_STEP(16, 16, false, 3);
+        if (C == 12) NFB_STEP(16, 16, false, 12);
+    } else if (h == 8 && w == 8) {
+        if (C == 12) { if (pair) NFB_STEP(8, 8, true, 12); NFB_STEP(8, 8, false, 12); }
+    }
+    // C = 48 (8x8 / 4x4 conditioner maps): measured slower inside this kernel (2304 FMAs per pixel on the 256 epilogue
+    // threads of <= 128 CTAs) than as its own launch on every SM -- left to nfb_actnorm_invconv_fwd
+#undef NFB_STEP
+    return NFB_ERR_UNSUPPORTED;
+}
+
+int convnet_affine_step_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
+                                    int B, const float* sa, const float* sb, const float* an_ls, const float* an_b,
+                                    const float* Wm, const float* log_s, int flags, cudaStream_t st) {
+    if (Cout != 2 * g.c0) return NFB_ERR_SHAPE;
+    const PostOp post{an_ls, an_b, Wm, log_s};
+    if (mode == NFB_SPLIT_CHECKER) return tc_step_by_size<NFB_SPLIT_CHECKER>(z, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st, post);
+    if (mode == NFB_SPLIT_CHANNEL) return tc_step_by_size<NFB_SPLIT_CHANNEL>(z, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st, post);
     return NFB_ERR_UNSUPPORTED;
 }
 

@@ -191,6 +191,122 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
     }
 }
 
+// ---- apply, large C (multiples of 64; C = 192 is the last level of a 64x64 Glow): the C x C matrix no longer fits next to a
+// useful pixel tile, and re-staging it per (sample, pixel tile) made the launch L2-bound by ~100x.  Here a CTA owns a tile of
+// CT = 64 OUTPUT channels, keeps that slice of the matrix (C x 64) in shared memory for its whole life and walks over
+// (sample, 64-pixel tile) units, persistent; thread = 4 output channels x 4 pixels, the same ascending-ci fmaf chain as
+// invconv_apply_tiled (bit-identical results).
+template <int ACTNORM>
+__global__ void __launch_bounds__(256, 2) invconv_apply_cotile(const float* __restrict__ zin, float* __restrict__ zout,
+                                                              const float* ldj_in, float* ldj_out,
+                                                              const float* __restrict__ M, const float* __restrict__ log_s,
+                                                              const float* __restrict__ an_log_scale,
+                                                              const float* __restrict__ an_bias, float sign, int B, int C,
+                                                              int HW, int TP) {
+    constexpr int CT = 64;
+    extern __shared__ __align__(16) float sm[];
+    float* Mt = sm;             // [C][CT]: Mt[ci][co - co0] = M[co][ci]
+    float* zs = sm + C * CT;    // [C][TP]
+    float* ane = zs + C * TP;   // ACTNORM == 1: exp(log_scale)[C], bias[C]
+    const int co0 = blockIdx.y * CT;
+    for (int i = threadIdx.x; i < C * CT; i += blockDim.x) {
+        const int co = i / C, ci = i - co * C;  // coalesced reads of M's rows
+        Mt[ci * CT + co] = __ldg(M + static_cast<size_t>(co0 + co) * C + ci);
+    }
+    if (ACTNORM == 1)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { ane[c] = expf(__ldg(an_log_scale + c)); ane[C + c] = __ldg(an_bias + c); }
+    const int tiles = (HW + TP - 1) / TP;
+    const int tpv = TP >> 2;
+    const int cg = threadIdx.x / tpv, pv = threadIdx.x - cg * tpv;  // 256 threads = (CT / 4 = 16 channel groups) x (TP / 4 quads)
+    for (int unit = blockIdx.x; unit < B * tiles; unit += gridDim.x) {
+        const int b = unit / tiles, p0 = (unit - b * tiles) * TP;
+        const int tp = (HW - p0) < TP ? (HW - p0) : TP;
+        __syncthreads();  // Mt / ane staged (first unit); everyone finished reading zs (later units)
+        const float* zb = zin + static_cast<size_t>(b) * C * HW + p0;
+        for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
+            const int ci = i / tpv, q = i - ci * tpv;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < tp) {
+                v = ldg4(zb + static_cast<size_t>(ci) * HW + 4 * q);
+                if (ACTNORM == 1) {
+                    const float e = ane[ci], bi = ane[C + ci];
+                    v.x = __fdiv_rn(__fsub_rn(v.x, bi), e);
+                    v.y = __fdiv_rn(__fsub_rn(v.y, bi), e);
+                    v.z = __fdiv_rn(__fsub_rn(v.z, bi), e);
+                    v.w = __fdiv_rn(__fsub_rn(v.w, bi), e);
+                }
+            }
+            st4(zs + ci * TP + 4 * q, v);
+        }
+        if (ldj_out && blockIdx.y == 0 && p0 == 0 && threadIdx.x < 32) {
+            float part = 0.f, an = 0.f;
+            for (int c = threadIdx.x; c < C; c += 32) {
+                part += __ldg(log_s + c);
+                if (ACTNORM == 1) an -= __ldg(an_log_scale + c);
+                if (ACTNORM == 2) an += __ldg(an_log_scale + c);
+            }
+            part = warp_sum(part);
+            if (ACTNORM) an = warp_sum(an);
+            if (threadIdx.x == 0) {
+                float l = ldj_in[b];
+                if (ACTNORM == 1) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+                l = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+                if (ACTNORM == 2) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+                ldj_out[b] = l;
+            }
+        }
+        __syncthreads();
+        if (4 * pv < tp) {
+            float acc[4][4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
+            const float* mrow = Mt + cg * 4;
+            const float* zcol = zs + 4 * pv;
+#pragma unroll 8
+            for (int ci = 0; ci < C; ++ci) {
+                const float4 zv = ld4(zcol + ci * TP);
+                const float4 m = ld4(mrow + ci * CT);
+                const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    acc[o][0] = fmaf(mm[o], zv.x, acc[o][0]);
+                    acc[o][1] = fmaf(mm[o], zv.y, acc[o][1]);
+                    acc[o][2] = fmaf(mm[o], zv.z, acc[o][2]);
+                    acc[o][3] = fmaf(mm[o], zv.w, acc[o][3]);
+                }
+            }
+            float* ob = zout + (static_cast<size_t>(b) * C + co0 + cg * 4) * HW + p0 + 4 * pv;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (ACTNORM == 2) {
+                    const float e = expf(__ldg(an_log_scale + co0 + cg * 4 + o)), bi = __ldg(an_bias + co0 + cg * 4 + o);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[o][q] = __fadd_rn(__fmul_rn(acc[o][q], e), bi);
+                }
+                st4(ob + static_cast<size_t>(o) * HW, make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
+            }
+        }
+    }
+}
+
+template <int ACTNORM>
+static int launch_cotile(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
+                         const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
+                         cudaStream_t st) {
+    constexpr int CT = 64, TP = 64;  // 16 channel groups x 16 pixel quads = 256 threads
+    const size_t smem = (static_cast<size_t>(C) * CT + static_cast<size_t>(C) * TP + 2 * C) * 4;
+    if (smem > 110 * 1024) return -100;  // two CTAs per SM
+    auto kern = invconv_apply_cotile<ACTNORM>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const int tiles = (HW + TP - 1) / TP, ncot = C / CT;
+    long long units = static_cast<long long>(B) * tiles;
+    long long gx = (2LL * kSMs + ncot - 1) / ncot;  // ~2 CTAs per SM in total
+    if (gx > units) gx = units;
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(ncot));
+    kern<<<grid, 256, smem, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, TP);
+    return launch_status();
+}
+
 template <int OCG, int ACTNORM>
 static int launch_tiled(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
                         const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
@@ -216,6 +332,10 @@ template <int ACTNORM>
 static int apply_dispatch(const float* z_in, float* z_out, const float* ldj_in, float* ldj_out, const float* M,
                           const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int C, int HW,
                           cudaStream_t st) {
+    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && C % 64 == 0 && C >= 128) {
+        const int rc = launch_cotile<ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
+        if (rc != -100) return rc;
+    }
     if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && B <= 65535) {
         int rc;
         if (C % 8 == 0 && C >= 96) rc = launch_tiled<8, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);

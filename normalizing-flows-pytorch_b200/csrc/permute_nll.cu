@@ -142,6 +142,35 @@ __global__ void __launch_bounds__(256) nll_rows_kernel(const float* __restrict__
     }
 }
 
+// Streaming batches (the batch alone fills the machine): one WARP per sample, no block barrier; every lane squares its
+// float4s in fp32 and adds them pairwise into an fp64 accumulator (one DADD per 4 elements), shuffle-reduced in fp64.
+__global__ void __launch_bounds__(256, 4) nll_rows_warp_kernel(const float* __restrict__ z, const float* __restrict__ ldj,
+                                                              float* __restrict__ nll_rows, int B, int D) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+        const float* zr = z + static_cast<size_t>(row) * D;
+        double acc = 0.0;
+        const int n4 = D >> 2;
+        int i = lane;
+        for (; i + 96 < n4; i += 128) {  // four independent 16-byte loads in flight
+            const float4 a = ldg4(zr + 4 * i), b = ldg4(zr + 4 * (i + 32)), c = ldg4(zr + 4 * (i + 64)), d = ldg4(zr + 4 * (i + 96));
+            acc += static_cast<double>(fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w));
+            acc += static_cast<double>(fmaf(b.x, b.x, b.y * b.y) + fmaf(b.z, b.z, b.w * b.w));
+            acc += static_cast<double>(fmaf(c.x, c.x, c.y * c.y) + fmaf(c.z, c.z, c.w * c.w));
+            acc += static_cast<double>(fmaf(d.x, d.x, d.y * d.y) + fmaf(d.z, d.z, d.w * d.w));
+        }
+        for (; i < n4; i += 32) {
+            const float4 a = ldg4(zr + 4 * i);
+            acc += static_cast<double>(fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const double nll = 0.5 * acc + 0.5 * static_cast<double>(D) * 1.8378770664093453 - static_cast<double>(__ldg(ldj + row));
+            nll_rows[row] = static_cast<float>(nll);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) nll_sum_kernel(const float* __restrict__ rows, double* sum_out, int B) {
     __shared__ double red[33];
     double tot = 0.0;
@@ -207,8 +236,14 @@ extern "C" int nfb_gauss_nll(const float* z, const float* ldj, float* nll_rows, 
     if (!z || !ldj || !nll_rows) return NFB_ERR_NULL;
     if (B <= 0 || D <= 0) return NFB_ERR_SHAPE;
     cudaStream_t st = as_stream(stream);
-    const int grid = B < kSMs * 8 ? B : kSMs * 8;
-    nll_rows_kernel<<<grid, D >= 1024 ? 256 : 64, 0, st>>>(z, ldj, nll_rows, B, D);
+    if (B >= kSMs * 64 && D >= 512 && (D & 3) == 0 && aligned16(z)) {
+        long long grid = (static_cast<long long>(B) + 7) / 8;
+        if (grid > kSMs * 64) grid = kSMs * 64;
+        nll_rows_warp_kernel<<<static_cast<int>(grid), 256, 0, st>>>(z, ldj, nll_rows, B, D);
+    } else {
+        const int grid = B < kSMs * 8 ? B : kSMs * 8;
+        nll_rows_kernel<<<grid, D >= 1024 ? 256 : 64, 0, st>>>(z, ldj, nll_rows, B, D);
+    }
     const int rc = launch_status();
     if (rc != NFB_OK || !sum_out) return rc;
     nll_sum_kernel<<<1, 1024, 0, st>>>(nll_rows, sum_out, B);  // single CTA, fixed order: deterministic

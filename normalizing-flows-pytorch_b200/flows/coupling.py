@@ -107,10 +107,11 @@ class AffineCoupling(AbstractCoupling):
     # conditioner + bijection + log-det as ONE tensor-core kernel (nfb_convnet_affine_fwd); False = two kernels
     fused_conditioner = True
 
-    def forward_fused(self, z, ldj, inplace=False):
+    def forward_fused(self, z, ldj, inplace=False, post=None):
         """ConvNet conditioner and the affine transform as one kernel; (t, s) never leave the SM.  The kernel works in
         place on z: `inplace=False` (the layer API) first copies z so that the caller's tensor is left alone, like the
-        reference's merged output; `Compose` passes inplace=True for a z it owns.  None: shape / mode not covered."""
+        reference's merged output; `Compose` passes inplace=True for a z it owns.  post = (ActNorm, InvertibleConv1x1) of
+        the NEXT flow step: applied by the same kernel (nfb_convnet_affine_step_fwd).  None: shape / mode not covered."""
         if (not self.fused_conditioner or z.dim() != 4 or self.net.training or type(self.net) is not ConvNet
                 or self._recording(z, ldj)):
             return None
@@ -119,9 +120,17 @@ class AffineCoupling(AbstractCoupling):
         if (h, w) not in ((16, 16), (8, 8), (4, 4)) or B == 0:
             return None
         out = z if inplace else z.clone()
-        rc = L.lib().nfb_convnet_affine_fwd(L.ptr(out), L.ptr(ldj), L.ptr(self.net.packed()),
-                                            L.ptr(self.s_log_scale.data), L.ptr(self.s_bias.data), B, C, H, W, self.mode,
-                                            int(self.odd), int(self.net.kernel_flags), L.stream())
+        if post is not None:
+            an, conv = post
+            rc = L.lib().nfb_convnet_affine_step_fwd(L.ptr(out), L.ptr(ldj), L.ptr(self.net.packed()),
+                                                     L.ptr(self.s_log_scale.data), L.ptr(self.s_bias.data),
+                                                     L.ptr(an.log_scale.data), L.ptr(an.bias.data), L.ptr(conv.matrices()[0]),
+                                                     L.ptr(conv.log_s.data), B, C, H, W, self.mode, int(self.odd),
+                                                     int(self.net.kernel_flags), L.stream())
+        else:
+            rc = L.lib().nfb_convnet_affine_fwd(L.ptr(out), L.ptr(ldj), L.ptr(self.net.packed()),
+                                                L.ptr(self.s_log_scale.data), L.ptr(self.s_bias.data), B, C, H, W, self.mode,
+                                                int(self.odd), int(self.net.kernel_flags), L.stream())
         if rc == L.ERR_UNSUPPORTED:
             return None
         L.check(rc)

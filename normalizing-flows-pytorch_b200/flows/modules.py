@@ -296,8 +296,10 @@ def _invconv_actnorm_inv(an, conv, y, log_df_dz):
 class Compose(nn.Module):
     """modules.py:325-339: sequential / reversed application."""
 
-    # 1 (default): a Glow step is two launches -- ActNorm + 1x1 conv, then the tensor-core conditioner with the affine
-    # coupling as its epilogue, in place on the 1x1 conv's output; 0: every layer through its own forward()
+    # 1 (default): two launches per Glow step -- ActNorm + 1x1 conv, then the tensor-core conditioner with the affine coupling
+    # as its epilogue, in place; 2: the conditioner kernel also applies the NEXT step's ActNorm + 1x1 conv (one launch per
+    # step where C <= 12; measured on B200: no faster than 1 -- the per-pixel matrix product runs on the 256 epilogue threads
+    # of <= 148 CTAs instead of the whole machine -- so it is not the default); 0: every layer through its own forward()
     fuse_steps = 1
 
     def __init__(self, layers):
@@ -322,8 +324,17 @@ class Compose(nn.Module):
                     i += 2
                     owned = True
                     continue
-            # an affine coupling whose input this loop produced itself: conditioner + transform in place, one kernel
+            # an affine coupling whose input this loop produced itself: conditioner + transform in place, one kernel -- which
+            # also applies the NEXT step's ActNorm + 1x1 conv when those follow (a whole Glow step per launch)
             if fuse and owned and hasattr(layer, 'forward_fused'):
+                if (self.fuse_steps > 1 and i + 2 < n and type(layers[i + 1]) is ActNorm and layers[i + 1].initialized
+                        and type(layers[i + 2]) is InvertibleConv1x1):
+                    out = layer.forward_fused(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), inplace=True,
+                                              post=(layers[i + 1], layers[i + 2]))
+                    if out is not None:
+                        z, log_df_dz = out
+                        i += 3
+                        continue
                 out = layer.forward_fused(L.dev(z, 'z'), L.dev(log_df_dz, 'log_df_dz'), inplace=True)
                 if out is not None:
                     z, log_df_dz = out

@@ -70,6 +70,16 @@ cases.append(('affine 1-D D=64 (B=2^20)', lambda: L.check(L.lib().nfb_affine_cou
     L.SPLIT_1D, 0, st)), 12 * 64 + 8, 1 << 20))
 sq = torch.empty(B, 12, 16, 16, device='cuda')
 cases.append(('squeeze2d 3x32x32', lambda: L.check(L.lib().nfb_squeeze2d(z.data_ptr(), sq.data_ptr(), B, 3, 32, 32, 0, st)), 8 * D, B))
+# invertible 1x1 convolution, forward direction, alone and with the preceding ActNorm fused (8 D bytes per sample either way)
+for Cc, Hh in ((3, 32), (12, 16), (48, 8), (192, 4)):
+    zc = z.view(B, Cc, Hh, Hh)
+    oc = out.view(B, Cc, Hh, Hh)
+    Wc = torch.linalg.qr(torch.randn(Cc, Cc, device='cuda'))[0].contiguous()
+    lsc = torch.zeros(Cc, device='cuda')
+    cases.append(('invconv1x1 apply C=%d %dx%d' % (Cc, Hh, Hh), lambda zc=zc, oc=oc, Wc=Wc, lsc=lsc, Cc=Cc, Hh=Hh: L.check(L.lib().nfb_invconv1x1_apply(
+        zc.data_ptr(), oc.data_ptr(), ldj.data_ptr(), ldj.data_ptr(), Wc.data_ptr(), lsc.data_ptr(), 1.0, B, Cc, Hh * Hh, st)), 8 * D + 8))
+    cases.append(('actnorm+invconv fused C=%d %dx%d' % (Cc, Hh, Hh), lambda zc=zc, oc=oc, Wc=Wc, lsc=lsc, Cc=Cc, Hh=Hh: L.check(L.lib().nfb_actnorm_invconv_fwd(
+        zc.data_ptr(), oc.data_ptr(), ldj.data_ptr(), ldj.data_ptr(), lsc.data_ptr(), lsc.data_ptr(), Wc.data_ptr(), lsc.data_ptr(), B, Cc, Hh * Hh, st)), 8 * D + 8))
 nr = torch.empty(B, device='cuda')
 tot = torch.empty(2, device='cuda', dtype=torch.float64)
 cases.append(('gauss_nll 3x32x32', lambda: L.check(L.lib().nfb_gauss_nll(z.data_ptr(), ldj.data_ptr(), nr.data_ptr(), tot.data_ptr(), B, D, st)), 4 * D + 8, B))

@@ -532,6 +532,34 @@ def test_fused_actnorm_invconv_is_bit_identical():
         assert torch.equal(y1, y2) and torch.equal(m1, m2), dims  # fused inverse == separate inverse layers
 
 
+@pytest.mark.parametrize('C,hw,B', [(192, 8, 5), (192, 8, 256), (128, 4, 9), (192, 16, 3), (256, 8, 2)])
+def test_invconv_large_channel_counts(C, hw, B):
+    """C >= 128 (the last level of a 64x64 Glow has C = 192): the co-tiled persistent kernel against a plain fp32 matrix
+    product, its fused-ActNorm variant against the two layers run one after the other (bit-identical), and the inverse."""
+    F = nfb().flows
+    torch.manual_seed(C + hw)
+    an, conv = F.ActNorm((C, hw, hw)), F.InvertibleConv1x1(C)
+    perturb_(an, 1)
+    perturb_(conv, 2)
+    an.initialized = True
+    an.to(DEV)
+    conv.to(DEV)
+    x = torch.randn(B, C, hw, hw, device=DEV)
+    l0 = torch.randn(B, device=DEV)
+    z, l = conv(x, l0.clone())
+    Wm = conv.matrices()[0]
+    ref = torch.einsum('oc,bcp->bop', Wm.double(), x.view(B, C, -1).double()).view_as(x)
+    close(z, ref.float(), rtol=2e-5, atol=2e-5 * float(ref.abs().max()), what='1x1 conv C=%d' % C)
+    close(l, l0 + conv.log_s.sum() * hw * hw, rtol=1e-5, atol=1e-3, what='ldj')
+    y, l2 = conv.backward(z, l.clone())
+    close(y, x, rtol=2e-4, atol=2e-4, what='inverse')
+    comp = F.Compose([an, conv]).to(DEV)
+    z1, l1 = comp(x, l0.clone())
+    comp.fuse_steps = 0
+    z2, l2 = comp(x, l0.clone())
+    assert torch.equal(z1, z2) and torch.equal(l1, l2)
+
+
 @pytest.mark.parametrize('key,values,cin,cout,hw', [(0, (0, 1), 6, 12, 16), (1, (0, 1, 2, 3), 24, 48, 8),
                                                     (2, (0, 1, 2, 3, 4), 96, 192, 4)])
 def test_convnet_variants_agree(key, values, cin, cout, hw):
@@ -632,6 +660,50 @@ def test_fused_conditioner_coupling(dims, masking, odd, B):
     scale = max(1.0, float(z3.abs().max()))
     close(z1, z3, rtol=2e-5, atol=4e-6 * scale, what='tensor-core vs ffma conditioner')
     close(l1, l3, rtol=2e-5, atol=4e-6 * max(1.0, float(l3.abs().max())), what='ldj tensor-core vs ffma')
+
+
+@pytest.mark.parametrize('dims,masking', [((3, 32, 32), 'checkerboard'), ((12, 16, 16), 'channelwise'),
+                                          ((12, 16, 16), 'checkerboard'), ((48, 8, 8), 'channelwise'),
+                                          ((48, 8, 8), 'checkerboard'), ((6, 16, 16), 'checkerboard')])
+@pytest.mark.parametrize('B', [1, 5, 256])
+@pytest.mark.parametrize('pair', [False, True])
+def test_whole_flow_step_in_one_launch(dims, masking, B, pair):
+    """Compose.fuse_steps = 2: [coupling i + ActNorm i+1 + 1x1 conv i+1] is ONE kernel (nfb_convnet_affine_step_fwd) -- against
+    fuse_steps = 1 (two kernels per step) and 0 (every layer on its own): z bit-identical (same fmaf chains), log-det to
+    rounding.  (6, 16, 16): a channel count without a fused variant -> falls back to two kernels, same result."""
+    n = nfb()
+    import nfb200._lib as L
+    torch.manual_seed(3)
+    layers = []
+    for i in range(3):
+        layers += [n.flows.ActNorm(dims), n.flows.InvertibleConv1x1(dims[0]), n.flows.AffineCoupling(dims, masking=masking, odd=i % 2 == 1)]
+    layers += [n.flows.ActNorm(dims), n.flows.InvertibleConv1x1(dims[0])]
+    comp = n.flows.Compose(layers)
+    perturb_(comp, 5)
+    for m in comp.modules():
+        if isinstance(m, n.flows.ActNorm):
+            m.initialized = True
+        if isinstance(m, n.flows.ConvNet) and pair:
+            m.kernel_flags = L.CONV_PAIR
+    comp.to(DEV).eval()
+    x = torch.randn((B, ) + dims, device=DEV)
+    l0 = torch.randn(B, device=DEV)
+    comp.fuse_steps = 2
+    comp(x, l0.clone())  # packs weights, builds W
+    n0 = n._lib.launch_count()
+    z2, l2 = comp(x, l0.clone())
+    launches = n._lib.launch_count() - n0
+    comp.fuse_steps = 1
+    z1, l1 = comp(x, l0.clone())
+    comp.fuse_steps = 0
+    z0, l0_ = comp(x, l0.clone())
+    assert torch.equal(z2, z1), float((z2 - z1).abs().max())
+    close(l2, l1, rtol=2e-6, atol=2e-3, what='ldj step-fused vs two kernels')
+    close(z2, z0, rtol=1e-5, atol=1e-5, what='z step-fused vs separate layers')
+    close(l2, l0_, rtol=2e-6, atol=2e-3, what='ldj step-fused vs separate layers')
+    if dims[0] in (3, 12):
+        assert launches == 4, launches  # ActNorm+conv | 3 x (coupling [+ next ActNorm+conv])
+    assert torch.equal(x, x)  # inputs untouched (Compose works on its own tensors)
 
 
 # ---------------------------------------------------------------------------------------------------------
