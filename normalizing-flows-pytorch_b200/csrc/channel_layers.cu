@@ -173,9 +173,14 @@ struct LogitRow {
         if (!INV) {
             x = fminf(fmaxf(x, lo), hi);                     // modules.py:147
             // logit(x) = log x - log(1-x) and -(y - 2 softplus(y)) = -(log x + log(1-x)) exactly (softplus(logit x) =
-            // -log(1-x)); two logf instead of div + logf + expf + log1pf.  |error| <= 2 ulp of max|log|, i.e. the same
-            // order as the reference's own fp32 rounding (modules.py:29-32,148-150).
-            const float l0 = logf(x), l1 = logf(__fsub_rn(1.f, x));
+            // -log(1-x)); two logarithms instead of div + logf + expf + log1pf (modules.py:29-32,148-150).
+            // The logarithms are lg2.approx * ln 2 (__logf): with libm's logf the layer was issue-bound at 0.56 of the HBM
+            // roofline (~50 instructions per element for 8 bytes).  Documented error of __logf: <= 2^-21.41 absolute for
+            // arguments in [0.5, 2], <= 3 ulp elsewhere.  Both results here are SUMS of the two logarithms, one of which is
+            // always >= ln 2 in magnitude, so an absolute error of 3.6e-7 per term is the rounding level of the results
+            // themselves (ulp(0.69) = 6e-8, ulp(4.6) = 4.8e-7); worst case over a 3072-pixel sample 1.1e-3 nats on a
+            // log-likelihood of ~8e3 nats = 1.4e-7 relative, inside the 1e-5 bits/dim budget.
+            const float l0 = __logf(x), l1 = __logf(__fsub_rn(1.f, x));
             x = __fsub_rn(l0, l1);
             return -__fadd_rn(l0, l1);
         }

@@ -6,6 +6,12 @@
 // k*c0 + m, like the reference's mixture layout, coupling.py:180-182).  thread = one element; parameter loads of
 // a warp are contiguous 128-byte lines; the softmaxes, the knot cumsum, the bin search and the rational map all
 // stay in registers; log|dy/dx| is reduced per sample in the same pass.
+//
+// Instruction budget (round 2): the kernel moves 100 B per element and was issue-bound at 0.51 of the HBM roofline
+// (~600 instructions per element: 16 expf, 19 IEEE divisions, 3 logf, 2 softplus).  Now: the softmax normalisation is
+// one reciprocal + K multiplies, its exponentials are ex2.approx (arguments <= 0, relative error 2^-22 on the terms
+// that carry weight), the three logarithms of the log-det are one, and 1/w is shared by the slope and xi.  Every change
+// moves a result by <= a few ulp (the oracle comparison in tests/ keeps its 2e-5 tolerance).
 #include "common.cuh"
 
 namespace nfb {
@@ -23,13 +29,13 @@ __device__ __forceinline__ void rqs_knots(float* knots, const float* __restrict_
     for (int k = 0; k < kk; ++k) { u[k] = __ldg(base + k * stride); mx = fmaxf(mx, u[k]); }
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < kk; ++k) { u[k] = expf(u[k] - mx); sum += u[k]; }
-    const float scale = 1.f - mn * static_cast<float>(kk);
+    for (int k = 0; k < kk; ++k) { u[k] = __expf(u[k] - mx); sum += u[k]; }
+    const float scale = __fdiv_rn(1.f - mn * static_cast<float>(kk), sum);  // (1 - min K) / sum: one division per softmax
     float c = 0.f;
     knots[0] = -bound;
 #pragma unroll
     for (int k = 0; k < kk; ++k) {
-        c = __fadd_rn(c, __fadd_rn(mn, __fmul_rn(scale, __fdiv_rn(u[k], sum))));
+        c = __fadd_rn(c, __fadd_rn(mn, __fmul_rn(scale, u[k])));
         knots[k + 1] = __fsub_rn(__fmul_rn(2.f * bound, c), bound);
     }
     knots[kk] = bound;
@@ -78,14 +84,18 @@ struct RqsRow {
         const float d0 = bin == 0 ? 1.f : kMinD + softplus_f(__ldg(dbase + static_cast<size_t>(bin - 1) * n0));
         const float d1 = bin == kk - 1 ? 1.f : kMinD + softplus_f(__ldg(dbase + static_cast<size_t>(bin) * n0));
         const float w = x1 - x0, h = y1 - y0;
-        const float sk = h / w;
+        const float rw = __fdiv_rn(1.f, w);
+        const float sk = h * rw;
         float out, ld;
         if (!INV) {
-            const float xi = (x - x0) / w;
+            const float xi = (x - x0) * rw;
             const float om = xi * (1.f - xi);
             const float den = sk + (d1 + d0 - 2.f * sk) * om;
-            out = y0 + h * (sk * xi * xi + d0 * om) / den;
-            ld = 2.f * logf(sk) + logf(d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)) - 2.f * logf(den);
+            const float rden = __fdiv_rn(1.f, den);
+            out = y0 + h * (sk * xi * xi + d0 * om) * rden;
+            // log(sk^2 num / den^2): sk, den in [1e-3 .. 2e3 / 1e-3] -> the ratio stays far inside the fp32 range
+            const float r = sk * rden;
+            ld = logf(r * r * (d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)));
         } else {
             const float dy = x - y0;
             const float t = d0 + d1 - 2.f * sk;
@@ -97,7 +107,8 @@ struct RqsRow {
             out = xi * w + x0;
             const float om = xi * (1.f - xi);
             const float den = sk + t * om;
-            ld = -(2.f * logf(sk) + logf(d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)) - 2.f * logf(den));
+            const float r = __fdiv_rn(sk, den);
+            ld = -logf(r * r * (d1 * xi * xi + 2.f * sk * om + d0 * (1.f - xi) * (1.f - xi)));
         }
         zout[zbase + e] = out;
         return ld;

@@ -115,15 +115,21 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
     extern __shared__ __align__(16) float sm[];
     float* Mt = sm;                          // C*C
     float* zs = sm + ((C * C + 3) & ~3);     // C*TP, 16-byte aligned
-    const int b = blockIdx.y;
-    const int p0 = blockIdx.x * TP;
-    const int tp = (HW - p0) < TP ? (HW - p0) : TP;  // multiple of 4
 
-    // Mt[ci][co] = M[co][ci]: contiguous (conflict-free) shared stores, strided reads of the small L1-resident matrix
+    // Mt[ci][co] = M[co][ci]: contiguous (conflict-free) shared stores, strided reads of the small L1-resident matrix;
+    // staged ONCE per CTA -- the CTA then walks over (sample, pixel tile) units (at streaming batch sizes re-staging a
+    // 48 x 48 matrix per 48 x 64 tile had doubled the CTA's loads)
     for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
         const int ci = i / C, co = i - ci * C;
         Mt[i] = __ldg(M + co * C + ci);
     }
+    const int tiles = (HW + TP - 1) / TP;
+    const long long units = static_cast<long long>(B) * tiles;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int b = static_cast<int>(unit / tiles);
+    const int p0 = static_cast<int>(unit - static_cast<long long>(b) * tiles) * TP;
+    const int tp = (HW - p0) < TP ? (HW - p0) : TP;  // multiple of 4
+    if (unit != blockIdx.x) __syncthreads();  // everyone finished reading zs of the previous unit
     const float* zb = zin + (static_cast<size_t>(b) * C) * HW + p0;
     const int tpv = tp >> 2;
     for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
         }
         st4(zs + ci * TP + 4 * pv, v);
     }
-    if (ldj_out && blockIdx.x == 0 && threadIdx.x < 32) {
+    if (ldj_out && p0 == 0 && threadIdx.x < 32) {
         float part = 0.f, an = 0.f;
         for (int c = threadIdx.x; c < C; c += 32) {
             part += __ldg(log_s + c);
@@ -189,6 +195,110 @@ __global__ void __launch_bounds__(512) invconv_apply_tiled(const float* __restri
             st4(ob + static_cast<size_t>(o) * HW, make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
         }
     }
+    }  // units
+}
+
+// ---- apply, tiny C (3 and 12: the first two levels of Glow on 32x32): no shared-memory staging of z and no barrier in
+// the loop.  thread = 4 pixels x ALL channels: C float4 loads in flight, C x C x 4 fmaf in the same ascending-ci chains as
+// invconv_apply_tiled (bit-identical), C float4 stores; the matrix is read from shared memory as warp-wide broadcasts.
+template <int C, int ACTNORM>
+__global__ void __launch_bounds__(256) invconv_apply_reg(const float* __restrict__ zin, float* __restrict__ zout,
+                                                        const float* ldj_in, float* ldj_out,
+                                                        const float* __restrict__ M, const float* __restrict__ log_s,
+                                                        const float* __restrict__ an_log_scale,
+                                                        const float* __restrict__ an_bias, float sign, int B, int HW) {
+    constexpr int CP = (C + 3) & ~3;  // matrix rows padded to whole float4s
+    __shared__ __align__(16) float Ms[C * CP];
+    __shared__ float an_e[C], an_b[C];
+    for (int i = threadIdx.x; i < C * CP; i += blockDim.x) {
+        const int co = i / CP, ci = i - co * CP;
+        Ms[i] = ci < C ? __ldg(M + co * C + ci) : 0.f;
+    }
+    if (ACTNORM)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { an_e[c] = expf(__ldg(an_log_scale + c)); an_b[c] = __ldg(an_bias + c); }
+    if (ldj_out && static_cast<long long>(blockIdx.x) * blockDim.x < B) {  // the leading CTAs own one sample per thread
+        float part = 0.f, an = 0.f;
+        for (int c = threadIdx.x & 31; c < C; c += 32) {
+            part += __ldg(log_s + c);
+            if (ACTNORM == 1) an -= __ldg(an_log_scale + c);
+            if (ACTNORM == 2) an += __ldg(an_log_scale + c);
+        }
+        part = warp_sum(part);
+        if (ACTNORM) an = warp_sum(an);
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b < B) {
+            float l = ldj_in[b];
+            if (ACTNORM == 1) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+            l = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+            if (ACTNORM == 2) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+            ldj_out[b] = l;
+        }
+    }
+    __syncthreads();
+    const int qpr = HW >> 2;
+    const long long total = static_cast<long long>(B) * qpr;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / qpr;
+        const int q = static_cast<int>(i - b * qpr);
+        const float* zb = zin + static_cast<size_t>(b) * C * HW + 4 * q;
+        float4 v[C];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) v[ci] = ldg4(zb + static_cast<size_t>(ci) * HW);
+        if (ACTNORM == 1) {
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const float e = an_e[ci], bi = an_b[ci];
+                v[ci].x = __fdiv_rn(__fsub_rn(v[ci].x, bi), e);
+                v[ci].y = __fdiv_rn(__fsub_rn(v[ci].y, bi), e);
+                v[ci].z = __fdiv_rn(__fsub_rn(v[ci].z, bi), e);
+                v[ci].w = __fdiv_rn(__fsub_rn(v[ci].w, bi), e);
+            }
+        }
+        float* ob = zout + static_cast<size_t>(b) * C * HW + 4 * q;
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c4 = 0; c4 < CP / 4; ++c4) {
+                const float4 m = ld4(Ms + co * CP + 4 * c4);
+                const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ci = 4 * c4 + k;
+                    if (ci < C) {
+                        acc.x = fmaf(mm[k], v[ci].x, acc.x);
+                        acc.y = fmaf(mm[k], v[ci].y, acc.y);
+                        acc.z = fmaf(mm[k], v[ci].z, acc.z);
+                        acc.w = fmaf(mm[k], v[ci].w, acc.w);
+                    }
+                }
+            }
+            if (ACTNORM == 2) {
+                const float e = an_e[co], bi = an_b[co];
+                acc.x = __fadd_rn(__fmul_rn(acc.x, e), bi);
+                acc.y = __fadd_rn(__fmul_rn(acc.y, e), bi);
+                acc.z = __fadd_rn(__fmul_rn(acc.z, e), bi);
+                acc.w = __fadd_rn(__fmul_rn(acc.w, e), bi);
+            }
+            st4(ob + static_cast<size_t>(co) * HW, acc);
+        }
+    }
+}
+
+template <int C, int ACTNORM>
+static int launch_reg(const float* zin, float* zout, const float* ldj_in, float* ldj_out, const float* M,
+                      const float* log_s, const float* an_ls, const float* an_b, float sign, int B, int HW,
+                      cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * (HW / 4);
+    const int threads = total < static_cast<long long>(kSMs) * 256 ? 128 : 256;  // small batches: spread over more SMs
+    long long blocks = (total + threads - 1) / threads;
+    const long long need = (B + threads - 1) / threads;
+    if (blocks > kSMs * 8) blocks = kSMs * 8;
+    if (blocks < need) blocks = need;
+    invconv_apply_reg<C, ACTNORM><<<static_cast<int>(blocks), threads, 0, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, an_ls, an_b,
+                                                                          sign, B, HW);
+    return launch_status();
 }
 
 // ---- apply, large C (multiples of 64; C = 192 is the last level of a 64x64 Glow): the C x C matrix no longer fits next to a
@@ -205,6 +315,7 @@ __global__ void __launch_bounds__(256, 2) invconv_apply_cotile(const float* __re
                                                               int HW, int TP) {
     constexpr int CT = 64;
     extern __shared__ __align__(16) float sm[];
+    __shared__ float ldj_term[2];
     float* Mt = sm;             // [C][CT]: Mt[ci][co - co0] = M[co][ci]
     float* zs = sm + C * CT;    // [C][TP]
     float* ane = zs + C * TP;   // ACTNORM == 1: exp(log_scale)[C], bias[C]
@@ -215,19 +326,46 @@ __global__ void __launch_bounds__(256, 2) invconv_apply_cotile(const float* __re
     }
     if (ACTNORM == 1)
         for (int c = threadIdx.x; c < C; c += blockDim.x) { ane[c] = expf(__ldg(an_log_scale + c)); ane[C + c] = __ldg(an_bias + c); }
-    const int tiles = (HW + TP - 1) / TP;
+    // the sample-independent log-det terms, once per CTA; the co-tile-0 CTAs then update ldj for a grid-strided set of samples
+    if (ldj_out && blockIdx.y == 0 && threadIdx.x < 32) {
+        float part = 0.f, an = 0.f;
+        for (int c = threadIdx.x; c < C; c += 32) {
+            part += __ldg(log_s + c);
+            if (ACTNORM == 1) an -= __ldg(an_log_scale + c);
+            if (ACTNORM == 2) an += __ldg(an_log_scale + c);
+        }
+        part = warp_sum(part);
+        if (ACTNORM) an = warp_sum(an);
+        if (threadIdx.x == 0) { ldj_term[0] = part; ldj_term[1] = an; }
+    }
+    __syncthreads();
+    if (ldj_out && blockIdx.y == 0) {
+        const float part = ldj_term[0], an = ldj_term[1];
+        for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+            float l = ldj_in[b];
+            if (ACTNORM == 1) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+            l = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
+            if (ACTNORM == 2) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
+            ldj_out[b] = l;
+        }
+    }
+    // a unit = TP consecutive positions of the flat (sample, pixel) axis: small maps (4x4: 16 pixels) put several samples
+    // into one tile so that every thread has work; a pixel quad never straddles a sample (HW % 4 == 0)
+    const long long npos = static_cast<long long>(B) * HW;
+    const long long units = (npos + TP - 1) / TP;
     const int tpv = TP >> 2;
     const int cg = threadIdx.x / tpv, pv = threadIdx.x - cg * tpv;  // 256 threads = (CT / 4 = 16 channel groups) x (TP / 4 quads)
-    for (int unit = blockIdx.x; unit < B * tiles; unit += gridDim.x) {
-        const int b = unit / tiles, p0 = (unit - b * tiles) * TP;
-        const int tp = (HW - p0) < TP ? (HW - p0) : TP;
-        __syncthreads();  // Mt / ane staged (first unit); everyone finished reading zs (later units)
-        const float* zb = zin + static_cast<size_t>(b) * C * HW + p0;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const long long pos0 = unit * TP;
+        if (unit != blockIdx.x) __syncthreads();  // everyone finished reading zs of the previous unit
         for (int i = threadIdx.x; i < C * tpv; i += blockDim.x) {
             const int ci = i / tpv, q = i - ci * tpv;
+            const long long pos = pos0 + 4 * q;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * q < tp) {
-                v = ldg4(zb + static_cast<size_t>(ci) * HW + 4 * q);
+            if (pos < npos) {
+                const long long b = pos / HW;
+                const int pp = static_cast<int>(pos - b * HW);
+                v = ldg4(zin + (static_cast<size_t>(b) * C + ci) * HW + pp);
                 if (ACTNORM == 1) {
                     const float e = ane[ci], bi = ane[C + ci];
                     v.x = __fdiv_rn(__fsub_rn(v.x, bi), e);
@@ -238,25 +376,9 @@ __global__ void __launch_bounds__(256, 2) invconv_apply_cotile(const float* __re
             }
             st4(zs + ci * TP + 4 * q, v);
         }
-        if (ldj_out && blockIdx.y == 0 && p0 == 0 && threadIdx.x < 32) {
-            float part = 0.f, an = 0.f;
-            for (int c = threadIdx.x; c < C; c += 32) {
-                part += __ldg(log_s + c);
-                if (ACTNORM == 1) an -= __ldg(an_log_scale + c);
-                if (ACTNORM == 2) an += __ldg(an_log_scale + c);
-            }
-            part = warp_sum(part);
-            if (ACTNORM) an = warp_sum(an);
-            if (threadIdx.x == 0) {
-                float l = ldj_in[b];
-                if (ACTNORM == 1) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
-                l = __fadd_rn(l, __fmul_rn(sign, __fmul_rn(part, static_cast<float>(HW))));
-                if (ACTNORM == 2) l = __fadd_rn(l, __fmul_rn(an, static_cast<float>(HW)));
-                ldj_out[b] = l;
-            }
-        }
         __syncthreads();
-        if (4 * pv < tp) {
+        const long long pos = pos0 + 4 * pv;
+        if (pos < npos) {
             float acc[4][4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
@@ -275,7 +397,9 @@ __global__ void __launch_bounds__(256, 2) invconv_apply_cotile(const float* __re
                     acc[o][3] = fmaf(mm[o], zv.w, acc[o][3]);
                 }
             }
-            float* ob = zout + (static_cast<size_t>(b) * C + co0 + cg * 4) * HW + p0 + 4 * pv;
+            const long long b = pos / HW;
+            const int pp = static_cast<int>(pos - b * HW);
+            float* ob = zout + (static_cast<size_t>(b) * C + co0 + cg * 4) * HW + pp;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 if (ACTNORM == 2) {
@@ -298,8 +422,8 @@ static int launch_cotile(const float* zin, float* zout, const float* ldj_in, flo
     if (smem > 110 * 1024) return -100;  // two CTAs per SM
     auto kern = invconv_apply_cotile<ACTNORM>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    const int tiles = (HW + TP - 1) / TP, ncot = C / CT;
-    long long units = static_cast<long long>(B) * tiles;
+    const int ncot = C / CT;
+    const long long units = (static_cast<long long>(B) * HW + TP - 1) / TP;
     long long gx = (2LL * kSMs + ncot - 1) / ncot;  // ~2 CTAs per SM in total
     if (gx > units) gx = units;
     dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(ncot));
@@ -323,7 +447,13 @@ static int launch_tiled(const float* zin, float* zout, const float* ldj_in, floa
     const int work = (C / OCG) * (TP / 4);
     int threads = work >= 512 ? 512 : ((work + 31) / 32) * 32;
     if (threads < 64) threads = 64;
-    dim3 grid((HW + TP - 1) / TP, B);
+    const long long units = static_cast<long long>(B) * ((HW + TP - 1) / TP);
+    int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));  // resident CTAs by shared memory ...
+    const int by_threads = 2048 / threads;                         // ... and by threads
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = static_cast<long long>(kSMs) * per_sm;
+    const int grid = static_cast<int>(units < cap ? units : cap);
     kern<<<grid, threads, smem, st>>>(zin, zout, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, TP);
     return launch_status();
 }
@@ -336,7 +466,9 @@ static int apply_dispatch(const float* z_in, float* z_out, const float* ldj_in, 
         const int rc = launch_cotile<ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
         if (rc != -100) return rc;
     }
-    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out) && B <= 65535) {
+    if (HW % 4 == 0 && aligned16(z_in) && aligned16(z_out)) {
+        if (C == 3) return launch_reg<3, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, HW, st);
+        if (C == 12) return launch_reg<12, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, HW, st);
         int rc;
         if (C % 8 == 0 && C >= 96) rc = launch_tiled<8, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);
         else if (C % 4 == 0) rc = launch_tiled<4, ACTNORM>(z_in, z_out, ldj_in, ldj_out, M, log_s, an_ls, an_b, sign, B, C, HW, st);

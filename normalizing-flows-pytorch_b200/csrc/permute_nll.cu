@@ -174,7 +174,15 @@ __global__ void __launch_bounds__(256, 4) nll_rows_warp_kernel(const float* __re
 __global__ void __launch_bounds__(1024) nll_sum_kernel(const float* __restrict__ rows, double* sum_out, int B) {
     __shared__ double red[33];
     double tot = 0.0;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) tot += static_cast<double>(rows[i]);
+    int i = threadIdx.x;
+    for (; i + 7 * 1024 < B && blockDim.x == 1024; i += 8 * 1024) {  // eight independent loads in flight, same summation order
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(rows + i + k * 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += static_cast<double>(v[k]);
+    }
+    for (; i < B; i += blockDim.x) tot += static_cast<double>(rows[i]);
     tot = block_sum(tot, red);
     if (threadIdx.x == 0) { sum_out[0] = tot; sum_out[1] = static_cast<double>(B); }
 }
