@@ -312,8 +312,9 @@ def dominant_kernel_probe(net, batch, peaks):
     """The kernels with the largest share of the step (profiles/r02_launches_glow32.md: ~85 %): the tensor-core ConvNet
     conditioner with the affine coupling as its epilogue (nfb_convnet_affine_fwd), one per conditioner shape.  Timed live,
     CUDA-graph replay of 20 back-to-back launches on inputs of the benchmark's size.  `achieved` counts the ALGORITHMIC
-    flops of the fp32 convolution stack (2 x MAC) -- the kernel issues 3 TF32 products per MAC
-    (error-compensated split precision), so its ceiling on this formulation is peak_tf32 / 3 = peak_bf16 / 6."""
+    flops of the fp32 convolution stack (2 x MAC) -- the kernel issues 3 half-precision products per MAC
+    (error-compensated FP16 split: hi*hi + hi*lo + lo*hi), so its ceiling on this formulation is peak_f16 / 3 (fp16 and bf16
+    share one tensor-pipe rate; MEASURED_PEAKS.json has the dense bf16 number)."""
     import nfb200
     from nfb200.flows.coupling import AffineCoupling
     seen, out, count = set(), [], {}
@@ -340,10 +341,10 @@ def dominant_kernel_probe(net, batch, peaks):
         us = graph_time_us(lambda: m.forward_fused(z, ldj, inplace=True))
         mac = h * w * (key[0] * 288 + 4 * 9216 + 32 * key[1])
         tf = 2 * mac * batch / us * 1e-6
-        out.append({'kernel': 'nfb_convnet_affine_fwd %dx%d in=%d out=%d (convnet_tc_kernel: tcgen05 3xTF32 + coupling epilogue)'
+        out.append({'kernel': 'nfb_convnet_affine_fwd %dx%d in=%d out=%d (convnet_tc_kernel: tcgen05 FP16-split x3 + coupling epilogue)'
                               % (h, w, key[0], key[1]),
                     'bound': 'tensor', 'us_per_launch': us, 'launches_per_step': count[key], 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak,
-                    'alg_flops_per_launch': 2 * mac * batch, 'frac_of_3xtf32_ceiling': tf / (peak / 6.0),
+                    'alg_flops_per_launch': 2 * mac * batch, 'frac_of_split_ceiling': tf / (peak / 3.0),
                     'traffic': _ncu('convnet_tc_%dx%d' % (h, w), 'dram_bytes_per_launch'),
                     'tensor_pipe_active_pct': _ncu('convnet_tc_%dx%d' % (h, w), 'tensor_pipe_active_pct'),
                     'peak_source': peaks['source'] + ' (dense bf16)'})

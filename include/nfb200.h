@@ -219,6 +219,7 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
  *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results */
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
+#define NFB_CONV_TF32 0x10000 /* tensor-core kernel with 3xTF32 operands instead of the default FP16 split */
 #define NFB_CONV_PAIR 0x80
 #define NFB_CONV_GROUPS_SHIFT 4
 #define NFB_CONV_GROUPS(g) ((g) << NFB_CONV_GROUPS_SHIFT)

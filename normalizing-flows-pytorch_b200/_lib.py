@@ -17,6 +17,7 @@ SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
 # kernel selection flags of nfb_convnet_fwd_ex / nfb_convnet_affine_fwd (include/nfb200.h)
 CONV_FFMA = 0x8
 CONV_PAIR = 0x80
+CONV_TF32 = 0x10000
 
 
 def conv_variant(v):

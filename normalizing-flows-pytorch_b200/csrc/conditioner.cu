@@ -476,7 +476,7 @@ template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                             int h, int w, int flags, cudaStream_t st) {
     if (!(flags & NFB_CONV_FFMA)) {  // default: tensor-core (tcgen05 3xTF32) kernel
-        const int rc = convnet_tc_dispatch(zsrc, out, pk + tc_plan(Cin, Cout).base, g, MODE, Cin, Cout, B, h, w, flags, st);
+        const int rc = convnet_tc_dispatch(zsrc, out, pk, g, MODE, Cin, Cout, B, h, w, flags, st);
         if (rc != NFB_ERR_UNSUPPORTED) return rc;
     }
     const int variant = flags & NFB_CONV_VARIANT_MASK;
@@ -597,7 +597,7 @@ using namespace nfb;
 extern "C" int nfb_resnet_pack_size(int in_ch, int out_ch, int conv) {
     if (in_ch <= 0 || out_ch <= 0) return NFB_ERR_SHAPE;
     if (!conv) return pack_layout(in_ch, out_ch, 1).total;
-    const TcPlan T = tc_plan(in_ch, out_ch);  // FFMA section followed by the tensor-core (3xTF32) section
+    const TcPlan T = tc_plan(in_ch, out_ch, 1);  // FFMA section | tensor-core 3xTF32 section | FP16-split section
     return T.base + T.total;
 }
 
@@ -636,7 +636,9 @@ extern "C" int nfb_resnet_pack(const float* const* t, float* packed, int in_ch, 
     if ((rc = bn(4, packed + L.bnO))) return rc;
     if ((rc = wn(5, -1, packed + L.wout, packed + L.bout, out_ch, kF, CoutPad))) return rc;
     if (!conv) return NFB_OK;
-    return pack_tc_launch(packed, packed + tc_plan(in_ch, out_ch).base, in_ch, out_ch, st);
+    const int rc_tc = pack_tc_launch(packed, packed + tc_plan(in_ch, out_ch, 0).base, in_ch, out_ch, 0, st);
+    if (rc_tc != NFB_OK) return rc_tc;
+    return pack_tc_launch(packed, packed + tc_plan(in_ch, out_ch, 1).base, in_ch, out_ch, 1, st);
 }
 
 extern "C" int nfb_convnet_fwd_ex(const float* src, float* params_out, const float* packed, int B, int C, int H, int W,
@@ -672,7 +674,7 @@ extern "C" int nfb_convnet_affine_fwd(float* z, float* ldj, const float* packed,
     if (rc != NFB_OK) return rc;
     if (mode != NFB_SPLIT_CHECKER && mode != NFB_SPLIT_CHANNEL) return NFB_ERR_UNSUPPORTED;
     if (flags & NFB_CONV_FFMA) return NFB_ERR_UNSUPPORTED;
-    return convnet_affine_tc_dispatch(z, ldj, packed + tc_plan(g.c0, 2 * g.c0).base, g, mode, g.c0, 2 * g.c0, B, s_log_scale,
+    return convnet_affine_tc_dispatch(z, ldj, packed, g, mode, g.c0, 2 * g.c0, B, s_log_scale,
                                       s_bias, flags, as_stream(stream));
 }
 
@@ -687,7 +689,7 @@ extern "C" int nfb_convnet_affine_step_fwd(float* z, float* ldj, const float* pa
     if (rc != NFB_OK) return rc;
     if (mode != NFB_SPLIT_CHECKER && mode != NFB_SPLIT_CHANNEL) return NFB_ERR_UNSUPPORTED;
     if (flags & NFB_CONV_FFMA) return NFB_ERR_UNSUPPORTED;
-    return convnet_affine_step_tc_dispatch(z, ldj, packed + tc_plan(g.c0, 2 * g.c0).base, g, mode, g.c0, 2 * g.c0, B,
+    return convnet_affine_step_tc_dispatch(z, ldj, packed, g, mode, g.c0, 2 * g.c0, B,
                                            s_log_scale, s_bias, next_log_scale, next_bias, next_W, next_log_s, flags,
                                            as_stream(stream));
 }

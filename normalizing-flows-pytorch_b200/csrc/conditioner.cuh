@@ -110,13 +110,18 @@ struct TcPlan {
     int NWg, nqg, NWf, nqf;  // output layer: columns per chunk (multiple of 16, <= 128) and chunks, generic / fused
     int consts, obias_g, obias_f, in0, mid0, outg, outf, total;
 };
-constexpr int kTcStageFloats = 9 * 4 * 512;  // one full 3x3 stage (72 KB)
-__host__ __device__ inline TcPlan tc_plan(int Cin, int Cout) {
+constexpr int kTcStageFloats = 9 * 4 * 512;  // one full 3x3 stage of the TF32 section (72 KB)
+// f16 = 1: the FP16-split section (appended after the TF32 section).  Same shared-memory images with 8 half-precision
+// channels per 16-byte row instead of 4 TF32 ones: a k-step covers 16 input channels, a full stage has 2 k-steps per tap
+// (36 KB), the lo parts are stored scaled by 2^kTcLoShift (conditioner_tc.cu).
+__host__ __device__ inline TcPlan tc_plan(int Cin, int Cout, int f16 = 0) {
     TcPlan P;
+    const int KS = f16 ? 16 : 8, NJ = 32 / KS;  // channels per k-step, k-steps per tap of a 32-channel layer
+    const int stage = 9 * NJ * 512;
     P.base = (pack_layout(Cin, Cout, 9).total + 31) & ~31;
     P.n_in = (Cin + kF - 1) / kF;
     const int last = Cin - (P.n_in - 1) * kF;
-    P.nj_last = ((last + 7) & ~7) / 8;
+    P.nj_last = (last + KS - 1) / KS;
     P.nqg = (Cout + 127) / 128;
     P.NWg = (((Cout + P.nqg - 1) / P.nqg) + 15) & ~15;
     if (Cout % 2 == 0) {
@@ -131,11 +136,12 @@ __host__ __device__ inline TcPlan tc_plan(int Cin, int Cout) {
     P.consts = o; o += 352;
     P.obias_g = o; o += P.nqg * P.NWg;
     P.obias_f = o; o += P.nqf * P.NWf;
-    P.in0 = o; o += (P.n_in - 1) * kTcStageFloats + 9 * P.nj_last * 512;
-    P.mid0 = o; o += 4 * kTcStageFloats;
-    P.outg = o; o += P.nqg * 64 * P.NWg;
-    P.outf = o; o += P.nqf * 64 * P.NWf;
+    P.in0 = o; o += (P.n_in - 1) * stage + 9 * P.nj_last * 512;
+    P.mid0 = o; o += 4 * stage;
+    P.outg = o; o += P.nqg * 16 * NJ * P.NWg;
+    P.outf = o; o += P.nqf * 16 * NJ * P.NWf;
     P.total = o;
+    if (f16) P.base = tc_plan(Cin, Cout, 0).base + ((tc_plan(Cin, Cout, 0).total + 31) & ~31);
     return P;
 }
 // output channel behind column `col` of chunk `q` (-1: padding)
@@ -157,6 +163,6 @@ int convnet_affine_tc_dispatch(float* z, float* ldj, const float* pk_tc, const S
 int convnet_affine_step_tc_dispatch(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int mode, int Cin, int Cout,
                                     int B, const float* sa, const float* sb, const float* an_ls, const float* an_b,
                                     const float* Wm, const float* log_s, int flags, cudaStream_t st);
-int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st);
+int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, int f16, cudaStream_t st);
 
 }  // namespace nfb

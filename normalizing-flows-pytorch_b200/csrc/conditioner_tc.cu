@@ -15,6 +15,12 @@
 // with the instruction's disable-output-lane mask.  M utilisation is 100 % (16x16: 2 tiles per sample; 8x8: 2 samples
 // per tile; 4x4: 8 samples per tile).
 //
+// Operand format (default, round 2b): the FP16 split -- x = hi + 2^-10 lo' with hi = fp16(x), lo' = fp16(2^10 (x - hi)); the
+// same 11 + 11 significant bits and the same exact products as the TF32 split (the error against the fp64 oracle is the
+// same or smaller), but 2 bytes per operand element and K = 16 per instruction: half the shared-memory operand traffic
+// the issue loop was bound by, half the instructions, half the weight stages (36 KB), half the activation planes.
+// kind::tf32 operands (NFB_CONV_TF32) remain for data outside the fp16 range (|x| >= 65504 gives NaN outputs here).
+//
 // Accumulation: the tensor core adds into the fp32 accumulator with truncation, so a long MMA chain drifts by
 // ~(chain length) x 2^-24.  The k-steps of a layer are therefore spread over G accumulator groups (default 3: <= 13
 // chained MMAs), each [main 32 | compensation 32] columns, started by an unmasked centre-tap MMA with accumulate = 0
@@ -128,6 +134,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
         : "memory");
 }
+// same instruction with half-precision operands (K = 16 per instruction)
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                        uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void mma_any(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                        uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    if (F16) mma_f16(d_tmem, adesc, bdesc, idesc, accumulate, m0, m1, m2, m3);
+    else mma_tf32(d_tmem, adesc, bdesc, idesc, accumulate, m0, m1, m2, m3);
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -234,9 +258,28 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = tf32_rn(x - hi);
 }
 
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N as given (mma_sm100_desc.hpp bit layout)
+// FP16 split ("fp16x3"): x = hi + lo, hi = fp16_rn(x), lo' = fp16_rn((x - hi) * 2^kTcLoShift).  hi carries 11 significant
+// bits like TF32; the residual x - hi is exact in fp32 and at most 2^-11 |x|, so scaled by 2^10 it sits in the normal fp16
+// range for every |x| < 65504 (and for tiny x, where hi is a subnormal, the residual still holds the rest of x).  Products of
+// two fp16 numbers are exact in the fp32 accumulator exactly like TF32 ones; the compensation columns accumulate
+// 2^10 (a_hi w_lo + a_lo w_hi) and the epilogue scales them back.  Same error as 3xTF32 (oracle comparison in tests/), half
+// the operand bytes and half the instructions per input channel.  Saturating conversions: |x| >= 65504 degrades the
+// precision of that element, it never produces an infinity.
+constexpr int kTcLoShift = 10;
+constexpr float kLoScale = 1024.f, kLoInv = 1.f / 1024.f;
+__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));  // low half = x0 (the lower address)
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float l0 = (x0 - h0) * kLoScale, l1 = (x1 - h1) * kLoScale;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
+}
+
+// instruction descriptor: D = F32, A = B = TF32 (F16: half precision), both K-major, M = 128, N as given (mma_sm100_desc.hpp
+// bit layout: c_format bits 4-5, a_format 7-9, b_format 10-12; F16 = 0, TF32 = 2)
+template <bool F16 = false>
 __host__ __device__ constexpr uint32_t idesc_n(uint32_t n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // bit l of word wd set <=> lane 32*wd + l of tile t is a position whose tap (dy, dx) falls outside its image
@@ -284,7 +327,8 @@ struct Timeline {
 // tile 0 of a linked pair: dy = +1 taps last (they read tile 1's rows); tile 1: dy = -1 taps right after the centre
 // (they read tile 0's rows, which tile 0's epilogue overwrites once they are done)
 constexpr uint64_t kOrder0 = 0x876210534ull, kOrder1 = 0x876532104ull;
-constexpr int kSlotBytes = 9 * 4 * 2048;  // one 32->32 3x3 stage: [tap][k-step][2 x (64 rows x 16 B)]
+constexpr int kSlotBytes = 9 * 4 * 2048;  // one 32->32 3x3 stage: [tap][k-step][2 x (64 rows x 16 B)] (TF32; FP16 split: half)
+__host__ __device__ constexpr int slot_bytes(bool f16) { return f16 ? kSlotBytes / 2 : kSlotBytes; }
 constexpr int kEpiThreads = 256;
 constexpr int kThreads = 320;
 constexpr int kTileCols = 256;            // TMEM columns reserved per tile
@@ -293,7 +337,7 @@ constexpr int kTileCols = 256;            // TMEM columns reserved per tile
 // two tiles of a 16x16 sample (epilogue of one under the MMAs of the other, weights streamed once for both): ~1.5x the
 // work per SM-second of the single-tile unit, which leaves the tensor core idle during every epilogue, at the price of
 // half as many CTAs -- the choice when the batch (or several batches in flight) fills the machine anyway.
-template <int H, int W, bool PAIR>
+template <int H, int W, bool PAIR, bool F16 = false>
 struct TcGeom {
     static constexpr int HW = H * W;
     static constexpr bool LINKED = HW > 128 || PAIR;    // two tiles per unit, ping-pong (16x16: the two halves of a sample)
@@ -305,7 +349,9 @@ struct TcGeom {
     static constexpr int GUARD = W + 1;                 // positions before / after the tiles (tap offsets reach there)
     static constexpr int PB = 2 * GUARD + T * 128;      // positions per channel-chunk plane
     static constexpr int PS = PB * 16;                  // bytes per plane
-    static constexpr int ACT_BYTES = 16 * PS;           // 8 hi planes + 8 lo planes
+    static constexpr int NPL = F16 ? 4 : 8;             // planes of 16 B per position: 4 TF32 / 8 FP16 channels each
+    static constexpr int NJ = F16 ? 2 : 4;              // k-steps per tap of a 32-channel layer
+    static constexpr int ACT_BYTES = 2 * NPL * PS;      // hi planes + lo planes
     static_assert(T <= 2 && T * kTileCols <= 512, "unit exceeds TMEM");
     static_assert(HW == 256 || 128 % HW == 0, "tile must hold whole samples");
     static_assert(!(PAIR && HW > 128), "PAIR is for maps of at most 128 pixels");
@@ -325,20 +371,21 @@ struct PostOp {
     const float* log_s;         // (C)
 };
 
-template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP>
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
                   int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, PostOp post, int G, int dbg) {
-    using GM = TcGeom<H, W, PAIR>;
+    using GM = TcGeom<H, W, PAIR, F16>;
     constexpr int HW = GM::HW, T = GM::T, SPT = GM::SPT, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD,
-                  PB = GM::PB, PS = GM::PS;
+                  PB = GM::PB, PS = GM::PS, NPL = GM::NPL, NJ = GM::NJ;
     constexpr bool LINKED = GM::LINKED;
+    constexpr int SLOT = slot_bytes(F16);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* act = smem_raw;                              // [16 planes][PB][16 B]
-    unsigned char* ring = smem_raw + GM::ACT_BYTES;             // 2 x kSlotBytes
-    float* cst = reinterpret_cast<float*>(ring + 2 * kSlotBytes);
+    unsigned char* act = smem_raw;                              // [2 NPL planes][PB][16 B]
+    unsigned char* ring = smem_raw + GM::ACT_BYTES;             // 2 x SLOT
+    float* cst = reinterpret_cast<float*>(ring + 2 * SLOT);
 
-    const TcPlan P = tc_plan(Cin, Cout);
+    const TcPlan P = tc_plan(Cin, Cout, F16 ? 1 : 0);
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     uint64_t* bars = reinterpret_cast<uint64_t*>(cst + ((n_cst + 3) & ~3));
     // barrier indices
@@ -347,7 +394,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [8 warps][2]
     uint4* mask_tab = reinterpret_cast<uint4*>(red + 16);        // [T][9 taps]: rows of the tile whose tap leaves the image
     uint4* prog = mask_tab + 2 * 9;                              // [T][9 taps in issue order][mask, 4 k-steps]: see below
-    float* wpost = reinterpret_cast<float*>(prog + 2 * 9 * 5);   // CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
+    // (+ one spare table row: the issue loop reads one tap ahead); CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
+    float* wpost = reinterpret_cast<float*>(prog + (2 * 9 + 1) * 5);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
 
@@ -356,8 +404,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     tl_k.init(3, blockIdx.x == 0 && tid == 0);
     tl_k.stamp(0);
     const int NW = FUSED ? P.NWf : P.NWg, nq = FUSED ? P.nqf : P.nqg;
-    const int out_chunk_bytes = 256 * NW;
-    const int qps = kSlotBytes / out_chunk_bytes;               // out chunks per weight stage
+    const int out_chunk_bytes = 64 * NJ * NW;
+    const int qps = SLOT / out_chunk_bytes;                     // out chunks per weight stage
     const int n_out_stage = (nq + qps - 1) / qps;
     const int n_stage = P.n_in + 4 + n_out_stage;
     const int n_units = (B + SPU - 1) / SPU;
@@ -378,18 +426,18 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     // Issue program of a 32->32 3x3 layer (4 k-steps per tap): the operands of all 72 k-steps are the same in every such
     // layer, so they are tabulated once: per tap [lane mask | 4 x (A_hi descriptor lo word, A_lo descriptor lo word, B
     // offset inside the weight slot, TMEM column | accumulate << 31)] in the order the MMA lane issues them.
-    if (tid < T * 36) {
+    if (tid < T * 36 && (tid % 4) < NJ) {
         const int t = tid / 36, i = (tid % 36) / 4, j = tid % 4;
         const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
         const int tap = static_cast<int>((order >> (4 * i)) & 15u);
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const int Ge = G < 4 ? G : 4;
-        const int kc = 4 * i + j;
+        const int Ge = G < NJ ? G : NJ;
+        const int kc = NJ * i + j;
         const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128 + dy * W + dx);
         uint4 e;
         e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-        e.y = (((smem_u32(act + 8 * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-        e.z = static_cast<uint32_t>((tap * 4 + j) * 128);
+        e.y = (((smem_u32(act + NPL * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+        e.z = static_cast<uint32_t>((tap * NJ + j) * 128);
         e.w = static_cast<uint32_t>(t * kTileCols + (kc % Ge) * 64) | (kc >= Ge ? 0x80000000u : 0u);
         prog[(t * 9 + i) * 5 + 1 + j] = e;
         if (j == 0)
@@ -441,11 +489,11 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     size_t off;
                     uint32_t bytes;
                     if (s < P.n_in) {
-                        off = static_cast<size_t>(P.in0) * 4 + static_cast<size_t>(s) * kSlotBytes;
-                        bytes = (s == P.n_in - 1) ? 9u * P.nj_last * 2048u : static_cast<uint32_t>(kSlotBytes);
+                        off = static_cast<size_t>(P.in0) * 4 + static_cast<size_t>(s) * SLOT;
+                        bytes = (s == P.n_in - 1) ? 9u * P.nj_last * 2048u : static_cast<uint32_t>(SLOT);
                     } else if (s < P.n_in + 4) {
-                        off = static_cast<size_t>(P.mid0) * 4 + static_cast<size_t>(s - P.n_in) * kSlotBytes;
-                        bytes = kSlotBytes;
+                        off = static_cast<size_t>(P.mid0) * 4 + static_cast<size_t>(s - P.n_in) * SLOT;
+                        bytes = SLOT;
                     } else {
                         const int q0 = (s - P.n_in - 4) * qps;
                         const int nqs = (nq - q0) < qps ? (nq - q0) : qps;
@@ -454,7 +502,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     }
                     if (dbg & 32) { mbar_arrive(bar(W_FULL + slot)); continue; }  // profiling knob: no weight traffic
                     mbar_expect_tx(bar(W_FULL + slot), bytes);
-                    const uint32_t dst = smem_u32(ring + slot * kSlotBytes);
+                    const uint32_t dst = smem_u32(ring + slot * SLOT);
                     for (uint32_t o = 0; o < bytes; o += 18432u) {
                         const uint32_t n = (bytes - o) < 18432u ? (bytes - o) : 18432u;
                         bulk_g2s(dst + o, pkb + off + o, n, bar(W_FULL + slot));
@@ -470,7 +518,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         // bound, ~380 cycles per k-step.)
         if (elect_one()) {
             const uint64_t dAH = make_smem_desc(smem_u32(act), PS, 128);
-            const uint64_t dAL = make_smem_desc(smem_u32(act + 8 * PS), PS, 128);
+            const uint64_t dAL = make_smem_desc(smem_u32(act + NPL * PS), PS, 128);
             const bool no_mma = (dbg & 1) != 0, no_lo = (dbg & 4) != 0;
             uint32_t cnt = 0, ph_act0 = 0, ph_act1 = 0;
             Timeline tl;
@@ -493,10 +541,10 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     mbar_wait(bar(W_FULL + slot), (cnt >> 1) & 1u, 2);
                     tc_fence_after();
                     tl.stamp(2);
-                    const uint32_t wbase = smem_u32(ring + slot * kSlotBytes);
+                    const uint32_t wbase = smem_u32(ring + slot * SLOT);
                     if (s < P.n_in + 4) {
                         // ---- 3x3 layer ----
-                        const int nj = (s == P.n_in - 1) ? P.nj_last : 4;
+                        const int nj = (s == P.n_in - 1) ? P.nj_last : NJ;
                         const int Ge = G < nj ? G : nj;
                         const uint64_t dB = make_smem_desc(wbase, 1024, 128);
                         int kc = 0, rr = 0;  // k-steps issued into this tile's accumulators; round-robin group
@@ -504,34 +552,47 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         auto kstep = [&](uint32_t tbase, uint64_t a_hi, uint64_t a_lo, uint64_t b, const uint4& m) {
                             const uint32_t d = tbase + static_cast<uint32_t>(rr * 64);
                             if (!no_mma) {
-                                mma_tf32(d, a_hi, b, idesc_n(64), kc >= Ge ? 1u : 0u, m.x, m.y, m.z, m.w);
-                                if (!no_lo) mma_tf32(d + 32, a_lo, b, idesc_n(32), 1u, m.x, m.y, m.z, m.w);
+                                mma_any<F16>(d, a_hi, b, idesc_n<F16>(64), kc >= Ge ? 1u : 0u, m.x, m.y, m.z, m.w);
+                                if (!no_lo) mma_any<F16>(d + 32, a_lo, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
                             }
                             ++kc;
                             rr = (rr + 1 == Ge) ? 0 : rr + 1;
                         };
                         // taps order[i_lo .. i_hi) of tile t
                         auto issue = [&](int t, uint64_t order, int i_lo, int i_hi) {
-                            if (nj == 4) {
+                            if (nj == NJ) {
                                 // tabulated operands: 5 shared-memory loads feed 8 MMAs
                                 const uint32_t a_hi32 = (128u >> 4) | (1u << 14);
                                 const uint32_t b_hi32 = (128u >> 4) | (1u << 14);
                                 const uint32_t b_lo32 = ((wbase >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);
                                 const uint4* pt = prog + (t * 9 + i_lo) * 5;
+                                // software pipeline: the table entries of tap i + 1 are loaded before the MMAs of tap i are issued
+                                // (a single thread, `asm volatile` MMAs: nothing else hides the shared-memory latency; measured
+                                // ~140 cycles per tap without it)
+                                uint4 m = pt[0];
+                                uint4 e[NJ];
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) e[j] = pt[1 + j];
 #pragma unroll 1
-                                for (int i = i_lo; i < i_hi; ++i, pt += 5) {
-                                    const uint4 m = pt[0];
-                                    const uint4 e[4] = {pt[1], pt[2], pt[3], pt[4]};
+                                for (int i = i_lo; i < i_hi; ++i) {
+                                    pt += 5;  // the table has one spare row after the last tap of a tile (the next tile's / padding)
+                                    const uint4 m_n = pt[0];
+                                    uint4 e_n[NJ];
+#pragma unroll
+                                    for (int j = 0; j < NJ; ++j) e_n[j] = pt[1 + j];
                                     if (!no_mma) {
 #pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
+                                        for (int j = 0; j < NJ; ++j) {
                                             const uint64_t b = (static_cast<uint64_t>(b_hi32) << 32) | (b_lo32 + e[j].z);
                                             const uint32_t d = tmem + (e[j].w & 0xFFFFu);
-                                            mma_tf32(d, (static_cast<uint64_t>(a_hi32) << 32) | e[j].x, b, idesc_n(64), e[j].w >> 31, m.x, m.y, m.z, m.w);
+                                            mma_any<F16>(d, (static_cast<uint64_t>(a_hi32) << 32) | e[j].x, b, idesc_n<F16>(64), e[j].w >> 31, m.x, m.y, m.z, m.w);
                                             if (!no_lo)
-                                                mma_tf32(d + 32, (static_cast<uint64_t>(a_hi32) << 32) | e[j].y, b, idesc_n(32), 1u, m.x, m.y, m.z, m.w);
+                                                mma_any<F16>(d + 32, (static_cast<uint64_t>(a_hi32) << 32) | e[j].y, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
                                         }
                                     }
+                                    m = m_n;
+#pragma unroll
+                                    for (int j = 0; j < NJ; ++j) e[j] = e_n[j];
                                 }
                                 return;
                             }
@@ -566,7 +627,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         // ---- 1x1 output layer, chunks of NW columns: [main NW | comp NW] ----
                         const int q0 = (s - P.n_in - 4) * qps;
                         const int nqs = (nq - q0) < qps ? (nq - q0) : qps;
-                        const uint32_t i_main = idesc_n(static_cast<uint32_t>(2 * NW)), i_comp = idesc_n(static_cast<uint32_t>(NW));
+                        const uint32_t i_main = idesc_n<F16>(static_cast<uint32_t>(2 * NW)), i_comp = idesc_n<F16>(static_cast<uint32_t>(NW));
 #pragma unroll 1
                         for (int qi = 0; qi < nqs; ++qi) {
                             const uint64_t dB = make_smem_desc(wbase + static_cast<uint32_t>(qi * out_chunk_bytes),
@@ -576,12 +637,12 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                                 wait_act(t);
                                 const uint32_t d = tmem + static_cast<uint32_t>(t * kTileCols);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
+                                for (int j = 0; j < NJ; ++j) {
                                     const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128);
                                     const uint32_t b_off = static_cast<uint32_t>(j * 4 * NW);  // 2 blocks of 2NW rows x 16 B
                                     if (!no_mma) {
-                                        mma_tf32(d, dAH + a_off, dB + b_off, i_main, j > 0 ? 1u : 0u, 0u, 0u, 0u, 0u);
-                                        if (!no_lo) mma_tf32(d + NW, dAL + a_off, dB + b_off, i_comp, 1u, 0u, 0u, 0u, 0u);
+                                        mma_any<F16>(d, dAH + a_off, dB + b_off, i_main, j > 0 ? 1u : 0u, 0u, 0u, 0u, 0u);
+                                        if (!no_lo) mma_any<F16>(d + NW, dAL + a_off, dB + b_off, i_comp, 1u, 0u, 0u, 0u, 0u);
                                     }
                                 }
                                 commit(ACC_DONE + t);
@@ -647,17 +708,35 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                 tmem_ld16x2(t_lane + static_cast<uint32_t>(gi * 64) + col, t_lane + static_cast<uint32_t>(gi * 64 + 32) + col, m, cp);
                 if (gi == 0) {
 #pragma unroll
-                    for (int i = 0; i < EC; ++i) v[i] = m[i] + cp[i];
+                    for (int i = 0; i < EC; ++i) v[i] = F16 ? fmaf(cp[i], kLoInv, m[i]) : m[i] + cp[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < EC; ++i) v[i] += m[i] + cp[i];
+                    for (int i = 0; i < EC; ++i) v[i] += F16 ? fmaf(cp[i], kLoInv, m[i]) : m[i] + cp[i];
                 }
             }
             tl.stamp(36);
         };
+        // FP16 split: largest |activation| this thread has converted for the current unit.  At >= 65504 the conversion
+        // saturates and the sums that consumed it are wrong: the thread then returns NaN for its outputs (a loud failure;
+        // such data needs NFB_CONV_TF32), see the output layer.
+        float amax = 0.f;
         // a[EC] (activated) -> hi / lo planes of this thread's position
         auto store_act = [&](int sub, const float (&a)[EC]) {
             if (dbg & 16) return;  // profiling knob: no activation stores
+            if (F16) {
+#pragma unroll
+                for (int i = 0; i < EC; ++i) amax = fmaxf(amax, fabsf(a[i]));
+#pragma unroll
+                for (int c8 = 0; c8 < EC / 8; ++c8) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) split_f16_pair(a[c8 * 8 + 2 * q], a[c8 * 8 + 2 * q + 1], hi[q], lo[q]);
+                    const int plane = (ch0 + sub * EC) / 8 + c8;
+                    *reinterpret_cast<uint4*>(my_act + plane * PS) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(my_act + (NPL + plane) * PS) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                return;
+            }
 #pragma unroll
             for (int c4 = 0; c4 < EC / 4; ++c4) {
                 float hi[4], lo[4];
@@ -681,6 +760,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             tl.stamp(40);
             const int b = HW > 128 ? unit : unit * SPU + tile * SPT + row / HW;
             const bool valid = b < B;
+            amax = 0.f;
             const float* zb = zsrc + static_cast<size_t>(b) * (MODE < 0 ? static_cast<size_t>(Cin) * HW : static_cast<size_t>(g.D));
             float xres[NCH];
 
@@ -688,7 +768,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 #pragma unroll 1
             for (int c = 0; c < P.n_in; ++c) {
                 const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
-                const int n4 = ((CI + 7) & ~7) / 4;
+                const int n4 = F16 ? ((CI + 15) & ~15) / 4 : ((CI + 7) & ~7) / 4;
                 // this thread's share of the chunk: all loads first (they are independent: one round trip to L2), then the
                 // hi/lo split and the stores
                 constexpr int NG = 8 / CS;  // channel groups of 4 per thread
@@ -711,7 +791,15 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 #pragma unroll
                 for (int k = 0; k < NG; ++k) {
                     const int c4 = k * CS + (CS == 2 ? grp : 0);
-                    if (c4 < n4) {
+                    if (c4 < n4 && F16) {  // 4 channels = half of a 16-byte row of plane c4 / 2
+                        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(gv[k][0]), fabsf(gv[k][1]))), fmaxf(fabsf(gv[k][2]), fabsf(gv[k][3])));
+                        uint32_t hi[2], lo[2];
+                        split_f16_pair(gv[k][0], gv[k][1], hi[0], lo[0]);
+                        split_f16_pair(gv[k][2], gv[k][3], hi[1], lo[1]);
+                        unsigned char* dst = my_act + (c4 >> 1) * PS + (c4 & 1) * 8;
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2*>(dst + NPL * PS) = make_uint2(lo[0], lo[1]);
+                    } else if (c4 < n4) {
                         float hi[4], lo[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) split_tf32(gv[k][q], hi[q], lo[q]);
@@ -721,7 +809,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                 }
                 signal_act();
                 wait_acc();
-                const int nj = (c == P.n_in - 1) ? P.nj_last : 4;
+                const int nj = (c == P.n_in - 1) ? P.nj_last : NJ;
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
                     float v[EC];
@@ -755,7 +843,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
                     float v[EC], a[EC];
-                    load_acc(G < 4 ? G : 4, sub, v);  // conv1 (second BatchNorm of the block folded into weights and bias)
+                    load_acc(G < NJ ? G : NJ, sub, v);  // conv1 (second BatchNorm of the block folded into weights and bias)
 #pragma unroll
                     for (int i = 0; i < EC; ++i) a[i] = fmaxf(v[i] + c_blk(blk, 2)[ch0 + sub * EC + i], 0.f);
                     if (sub == 0) wait_war();
@@ -768,7 +856,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
                     float v[EC], a[EC];
-                    load_acc(G < 4 ? G : 4, sub, v);  // conv2 + skip
+                    load_acc(G < NJ ? G : NJ, sub, v);  // conv2 + skip
 #pragma unroll
                     for (int i = 0; i < EC; ++i) {
                         const int ch = ch0 + sub * EC + i;
@@ -798,6 +886,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                 }
             };
             if (FUSED) prefetch_z0(0);
+            const bool saturated = F16 && !(amax < 65504.f);
 #pragma unroll 1
             for (int q = 0; q < nq; ++q) {
                 wait_acc();
@@ -820,8 +909,9 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                             for (int r = 0; r < 4; ++r) {
                                 const int m = m0 + i + r;
                                 if (valid && m < g.c0) {
-                                    const float t = (tm[r] + tcp[r]) + ob[i + r];
-                                    const float sraw = (sm[r] + scp[r]) + ob[PC + i + r];
+                                    float t = (F16 ? fmaf(tcp[r], kLoInv, tm[r]) : tm[r] + tcp[r]) + ob[i + r];
+                                    float sraw = (F16 ? fmaf(scp[r], kLoInv, sm[r]) : sm[r] + scp[r]) + ob[PC + i + r];
+                                    if (saturated) t = sraw = __int_as_float(0x7fc00000);
                                     const int off = half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx);
                                     // coupling.py:107-109: two rounded ops each, no FMA contraction (as in coupling_affine.cu)
                                     const float s = __fadd_rn(__fmul_rn(tanhf(sraw), sa), sb);
@@ -841,8 +931,9 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         for (int r = 0; r < 4; ++r) {
                             const int m = m0 + i + r;
                             if (valid && m < g.c0) {
-                                const float t = (tm[r] + tcp[r]) + ob[i + r];
-                                const float sraw = (sm[r] + scp[r]) + ob[PC + i + r];
+                                float t = (F16 ? fmaf(tcp[r], kLoInv, tm[r]) : tm[r] + tcp[r]) + ob[i + r];
+                                float sraw = (F16 ? fmaf(scp[r], kLoInv, sm[r]) : sm[r] + scp[r]) + ob[PC + i + r];
+                                if (saturated) t = sraw = __int_as_float(0x7fc00000);
                                 const int off = half_elem_offset<(MODE < 0 ? NFB_SPLIT_CHANNEL : MODE)>(g, m, 0, yy, xx);
                                 const float s = __fadd_rn(__fmul_rn(tanhf(sraw), sa), sb);
                                 zo[off] = __fadd_rn(__fmul_rn(zo[off], expf(s)), t);
@@ -861,7 +952,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         for (int r = 0; r < 8; ++r) {
                             const int oc = q * NW + i + r;
                             if (valid && oc < Cout)
-                                zdst[(static_cast<size_t>(b) * Cout + oc) * HW + pix] = (mv[r] + cv[r]) + ob[i + r];
+                                zdst[(static_cast<size_t>(b) * Cout + oc) * HW + pix] =
+                                    saturated ? __int_as_float(0x7fc00000) : (F16 ? fmaf(cv[r], kLoInv, mv[r]) : mv[r] + cv[r]) + ob[i + r];
                         }
                     }
                 }
@@ -955,23 +1047,27 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
 // =====================================================================================================================
 // packing of the tensor-core section from the FFMA section (once per weight update)
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ pk, float* __restrict__ tc, int Cin, int Cout) {
+__global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ pk, float* __restrict__ tc, int Cin, int Cout,
+                                                      int f16) {
     const PackLayout L = pack_layout(Cin, Cout, 9);
-    const TcPlan P = tc_plan(Cin, Cout);
+    const TcPlan P = tc_plan(Cin, Cout, f16);
     const int c0 = Cout / 2;
+    const int NJ = f16 ? 2 : 4, KS = f16 ? 16 : 8;   // k-steps per tap of a 32-channel layer, channels per k-step
+    const int CPW = f16 ? 2 : 1;                     // input channels per 4-byte word
+    const int stage = 9 * NJ * 512;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.total; idx += gridDim.x * blockDim.x) {
-        float val = 0.f;
+        float val[2] = {0.f, 0.f};
         bool split = true, lo = false;
         if (idx < P.obias_g) {
             // constants: b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO
             const int k = idx - P.consts, c = k & 31;
-            if (k < 32) val = pk[L.b0 + c];
+            if (k < 32) val[0] = pk[L.b0 + c];
             else if (k < 288) {
                 const int blk = (k - 32) / 128, which = ((k - 32) % 128) / 32;
-                val = which == 0 ? pk[L.bnA[blk] + c] : which == 1 ? pk[L.bnA[blk] + kF + c]
-                      : which == 2 ? pk[L.b1[blk] + c] : pk[L.b2[blk] + c];
-            } else if (k < 320) val = pk[L.bnO + c];
-            else if (k < 352) val = pk[L.bnO + kF + c];
+                val[0] = which == 0 ? pk[L.bnA[blk] + c] : which == 1 ? pk[L.bnA[blk] + kF + c]
+                         : which == 2 ? pk[L.b1[blk] + c] : pk[L.b2[blk] + c];
+            } else if (k < 320) val[0] = pk[L.bnO + c];
+            else if (k < 352) val[0] = pk[L.bnO + kF + c];
             split = false;
         } else if (idx < P.in0) {
             // output bias by column: generic order, then fused order
@@ -979,78 +1075,93 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
             const int k = idx - (fused ? P.obias_f : P.obias_g);
             const int NW = fused ? P.NWf : P.NWg;
             const int oc = tc_out_channel(fused, k / NW, k % NW, NW, c0, Cout);
-            val = oc >= 0 ? pk[L.bout + oc] : 0.f;
+            val[0] = oc >= 0 ? pk[L.bout + oc] : 0.f;
             split = false;
         } else if (idx < P.outg) {
-            // 3x3 stages: [tap][j][k4][n (64: w_hi | w_lo)][4 ci]
+            // 3x3 stages: [tap][j][k-chunk 2][n (64: w_hi | w_lo)][16 bytes: 4 TF32 / 8 FP16 input channels]
             int e = idx - P.in0, cig_base, base, nj;
             if (idx < P.mid0) {
-                const int pass = e / (kSlotBytes / 4);
-                e -= pass * (kSlotBytes / 4);
-                nj = (pass == P.n_in - 1) ? P.nj_last : 4;
+                const int pass = e / stage;
+                e -= pass * stage;
+                nj = (pass == P.n_in - 1) ? P.nj_last : NJ;
                 cig_base = pass * kF;
                 base = -1;
             } else {
                 e = idx - P.mid0;
-                const int i = e / (kSlotBytes / 4);
-                e -= i * (kSlotBytes / 4);
-                nj = 4;
+                const int i = e / stage;
+                e -= i * stage;
+                nj = NJ;
                 cig_base = 0;
                 base = (i & 1) ? L.w2[i >> 1] : L.w1[i >> 1];
             }
-            const int ks = e / 512, r = e % 512;           // k-step (tap*nj + j), 512 floats each
+            const int ks = e / 512, r = e % 512;           // k-step (tap*nj + j), 512 words each
             const int tap = ks / nj, j = ks % nj;
-            const int k4 = r / 256, n = (r % 256) / 4, q = r % 4;
-            const int ci = cig_base + 8 * j + 4 * k4 + q, co = n & 31;
+            const int kch = r / 256, n = (r % 256) / 4, q = r % 4;
+            const int co = n & 31;
             lo = n >= 32;
-            if (base < 0) val = ci < Cin ? pk[L.w0 + (ci * 9 + tap) * kF + co] : 0.f;
-            else val = pk[base + (ci * 9 + tap) * kF + co];
+            for (int h = 0; h < CPW; ++h) {
+                const int ci = cig_base + KS * j + (KS / 2) * kch + CPW * q + h;
+                if (base < 0) val[h] = ci < Cin ? pk[L.w0 + (ci * 9 + tap) * kF + co] : 0.f;
+                else val[h] = pk[base + (ci * 9 + tap) * kF + co];
+            }
         } else {
-            // output chunks: [j][k4][n (2NW: hi | lo)][4 ci]
+            // output chunks: [j][k-chunk 2][n 2NW: hi | lo][16 bytes]
             const bool fused = idx >= P.outf;
             const int NW = fused ? P.NWf : P.NWg;
             const int e = idx - (fused ? P.outf : P.outg);
-            const int q_chunk = e / (64 * NW), r = e % (64 * NW);
-            const int blkk = r / (8 * NW), r2 = r % (8 * NW);  // block (j*2 + k4) of 2NW rows x 4 floats
+            const int q_chunk = e / (16 * NJ * NW), r = e % (16 * NJ * NW);
+            const int blkk = r / (8 * NW), r2 = r % (8 * NW);  // block (j*2 + k-chunk) of 2NW rows x 4 words
             const int n = r2 / 4, q = r2 % 4;
-            const int ci = 4 * blkk + q;
             lo = n >= NW;
             const int oc = tc_out_channel(fused, q_chunk, lo ? n - NW : n, NW, c0, Cout);
-            val = oc >= 0 ? pk[L.wout + ((oc >> 5) * kF + ci) * kF + (oc & 31)] : 0.f;  // pack_wn layout, J = 32
+            for (int h = 0; h < CPW; ++h) {
+                const int ci = (KS / 2) * blkk + CPW * q + h;
+                val[h] = oc >= 0 ? pk[L.wout + ((oc >> 5) * kF + ci) * kF + (oc & 31)] : 0.f;  // pack_wn layout, J = 32
+            }
         }
-        if (split) {
+        float out = val[0];
+        if (split && f16) {
+            uint32_t hi, l;
+            // a weight outside the fp16 range cannot be split: NaN makes every output of the network NaN (loud), see above
+            if (!(fabsf(val[0]) < 65504.f)) val[0] = __int_as_float(0x7fc00000);
+            if (!(fabsf(val[1]) < 65504.f)) val[1] = __int_as_float(0x7fc00000);
+            split_f16_pair(val[0], val[1], hi, l);
+            out = __uint_as_float(lo ? l : hi);
+        } else if (split) {
             float hi, l;
-            split_tf32(val, hi, l);
-            val = lo ? l : hi;
+            split_tf32(val[0], hi, l);
+            out = lo ? l : hi;
         }
-        tc[idx] = val;
+        tc[idx] = out;
     }
 }
 
-int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, cudaStream_t st) {
-    const TcPlan P = tc_plan(Cin, Cout);
+int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout, int f16, cudaStream_t st) {
+    const TcPlan P = tc_plan(Cin, Cout, f16);
     int blocks = (P.total + 255) / 256;
     if (blocks > kSMs * 8) blocks = kSMs * 8;
-    pack_tc_kernel<<<blocks, 256, 0, st>>>(pk_ffma, pk_tc_section, Cin, Cout);
+    pack_tc_kernel<<<blocks, 256, 0, st>>>(pk_ffma, pk_tc_section, Cin, Cout, f16);
     return launch_status();
 }
 
 // =====================================================================================================================
 // launch
 // =====================================================================================================================
-template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP = 0>
-static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
+// `packed` = the whole buffer of nfb_resnet_pack: FFMA section | TF32 section | FP16-split section
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP = 0, bool F16 = false>
+static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* packed, const SplitGeom& g, int Cin, int Cout, int B,
                      const float* sa, const float* sb, int flags, cudaStream_t st, const PostOp& post = PostOp{}) {
-    using GM = TcGeom<H, W, PAIR>;
+    using GM = TcGeom<H, W, PAIR, F16>;
     const int dbg = (flags >> NFB_CONV_DEBUG_SHIFT) & 0xff;
     const int gq = (flags >> NFB_CONV_GROUPS_SHIFT) & 7;
-    const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer
-    const TcPlan P = tc_plan(Cin, Cout);
+    const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer (at most the k-steps of a tap: 4 TF32 / 2 FP16)
+    const TcPlan P = tc_plan(Cin, Cout, F16 ? 1 : 0);
+    const float* pk_tc = packed + P.base;
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
-    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * kSlotBytes + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + 2 * 9 * 5 * 16 +
+    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * slot_bytes(F16) + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + (2 * 9 + 1) * 5 * 16 +
                         (CP > 0 ? static_cast<size_t>(CP * CP + 2 * CP + 4) * 4 : 0);
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
-    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP>;
+    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP, F16>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int n_units = (B + GM::SPU - 1) / GM::SPU;
     const int grid = n_units < kSMs ? n_units : kSMs;
@@ -1058,23 +1169,29 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pk
     return launch_status();
 }
 
-template <int MODE, bool FUSED>
-static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
-                      int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
-    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+template <int MODE, bool FUSED, bool F16>
+static int tc_by_size_p(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
+                        int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
+    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     // maps of <= 128 pixels: two tiles per CTA when asked for (NFB_CONV_PAIR: several batches in flight) or when the batch
     // alone gives every SM at least two single-tile units
     const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;
     const bool pair = (flags & NFB_CONV_PAIR) ? tiles >= 2 : tiles >= 2 * kSMs;
     if (h == 8 && w == 8) {
-        if (pair) return launch_tc<8, 8, MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
-        return launch_tc<8, 8, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        if (pair) return launch_tc<8, 8, MODE, FUSED, true, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        return launch_tc<8, 8, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     }
     if (h == 4 && w == 4) {
-        if (pair) return launch_tc<4, 4, MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
-        return launch_tc<4, 4, MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        if (pair) return launch_tc<4, 4, MODE, FUSED, true, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+        return launch_tc<4, 4, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     }
     return NFB_ERR_UNSUPPORTED;
+}
+template <int MODE, bool FUSED>
+static int tc_by_size(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
+                      int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
+    if (!(flags & NFB_CONV_TF32)) return tc_by_size_p<MODE, FUSED, true>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, h, w, sa, sb, flags, st);
+    return tc_by_size_p<MODE, FUSED, false>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, h, w, sa, sb, flags, st);
 }
 
 // conditioner + coupling + the next step's ActNorm / 1x1 conv: the (map size, channel count) pairs of the Glow stacks
@@ -1082,9 +1199,10 @@ template <int MODE>
 static int tc_step_by_size(float* z, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B, const float* sa,
                            const float* sb, int flags, cudaStream_t st, const PostOp& post) {
     const int h = g.h, w = g.w, C = g.C;
+    if (flags & NFB_CONV_TF32) return NFB_ERR_UNSUPPORTED;  // the step kernels exist for the default operand format only
     const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;
     const bool pair = (flags & NFB_CONV_PAIR) ? tiles >= 2 : tiles >= 2 * kSMs;
-#define NFB_STEP(H_, W_, PAIR_, CP_) return launch_tc<H_, W_, MODE, true, PAIR_, CP_>(z, z, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st, post)
+#define NFB_STEP(H_, W_, PAIR_, CP_) return launch_tc<H_, W_, MODE, true, PAIR_, CP_, true>(z, z, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st, post)
     if (h == 16 && w == 16) {
         if (C == 3) NFB_STEP(16, 16, false, 3);
         if (C == 12) NFB_STEP(16, 16, false, 12);

@@ -69,22 +69,23 @@ def convnet_case(cin, cout, hw, B, groups=(3, 1)):
     e_32 = float((ref32.double() - ref64).abs().max())
     line = 'convnet cin=%3d cout=%3d %2dx%-2d B=%4d | scale %.2f | cpu32 %.2e ffma %.2e (%.1f us)' % (
         cin, cout, hw, hw, B, scale, e_32, e_ff, t_ff)
-    for G in groups:
-        net.kernel_flags = L.conv_groups(G)
-        tc = net(xd)
-        torch.cuda.synchronize()
-        e_tc = float((tc[:nref].cpu().double() - ref64).abs().max())
-        d_all = float((tc - ffma).abs().max())
-        t_tc = timeit(lambda: net(xd))
-        line += ' | G=%d tc %.2e, vs ffma(all) %.2e (%.1f us)' % (G, e_tc, d_all, t_tc)
+    for name, base_flags, gs in (('tf32', L.CONV_TF32, groups), ('f16', 0, (2, 1))):
+        for G in gs:
+            net.kernel_flags = base_flags | L.conv_groups(G)
+            tc = net(xd)
+            torch.cuda.synchronize()
+            e_tc = float((tc[:nref].cpu().double() - ref64).abs().max())
+            d_all = float((tc - ffma).abs().max())
+            t_tc = timeit(lambda: net(xd))
+            line += ' | %s G=%d %.2e, vs ffma(all) %.2e (%.1f us)' % (name, G, e_tc, d_all, t_tc)
     net.kernel_flags = 0
     print(line, flush=True)
     if B == 256:
         line = '    knobs (us):'
-        for G in (3, 1):
+        for name, base_flags, G in (('tf32', L.CONV_TF32, 3), ('f16', 0, 2)):
             for dbg in (0, 1, 2, 4, 16, 32, 1 | 2, 1 | 2 | 16, 1 | 2 | 16 | 32, 2 | 16):
-                net.kernel_flags = L.conv_groups(G) | L.conv_debug(dbg)
-                line += ' G%d/%d=%.1f' % (G, dbg, timeit(lambda: net(xd)))
+                net.kernel_flags = base_flags | L.conv_groups(G) | L.conv_debug(dbg)
+                line += ' %s/%d=%.1f' % (name, dbg, timeit(lambda: net(xd)))
         net.kernel_flags = 0
         print(line, flush=True)
 
@@ -99,6 +100,7 @@ def fused_case(dims, masking, odd, B):
     l0 = torch.randn(B, device=DEV)
     with torch.no_grad():
         cpl.fused_conditioner = True
+        cpl.net.kernel_flags = L.CONV_TF32
         z1, l1 = cpl(x, l0.clone())
         t_f = timeit(lambda: cpl.forward_fused(x.clone(), l0.clone(), inplace=True))
         t_clone = timeit(lambda: (x.clone(), l0.clone()))
@@ -109,10 +111,20 @@ def fused_case(dims, masking, odd, B):
         z3, l3 = cpl(x, l0.clone())          # FFMA conditioner + coupling kernel
         t_3 = timeit(lambda: cpl(x, l0.clone()))
         cpl.net.kernel_flags = 0
+        cpl.fused_conditioner = True
+        z4, l4 = cpl(x, l0.clone())          # FP16-split fused kernel
+        t_4 = timeit(lambda: cpl.forward_fused(x.clone(), l0.clone(), inplace=True))
+        cpl.fused_conditioner = False
+        z5, l5 = cpl(x, l0.clone())          # FP16-split conditioner + coupling kernel
+        cpl.net.kernel_flags = L.CONV_PAIR
+        cpl.fused_conditioner = True
+        t_6 = timeit(lambda: cpl.forward_fused(x.clone(), l0.clone(), inplace=True))
+        cpl.net.kernel_flags = 0
     print('fused %s %s odd=%d B=%d | z: fused-vs-2k %.2e, fused-vs-ffma %.2e | ldj %.2e / %.2e | fused %.1f us (clone %.1f) '
-          '2-kernel %.1f us, ffma 2-kernel %.1f us' %
+          '2-kernel %.1f us, ffma 2-kernel %.1f us || f16: z vs ffma %.2e, fused-vs-2k %.2e, ldj %.2e, fused %.1f us, pair %.1f us' %
           (dims, masking, odd, B, float((z1 - z2).abs().max()), float((z1 - z3).abs().max()),
-           float((l1 - l2).abs().max()), float((l1 - l3).abs().max()), t_f, t_clone, t_2, t_3), flush=True)
+           float((l1 - l2).abs().max()), float((l1 - l3).abs().max()), t_f, t_clone, t_2, t_3,
+           float((z4 - z3).abs().max()), float((z4 - z5).abs().max()), float((l4 - l3).abs().max()), t_4, t_6), flush=True)
 
 
 if __name__ == '__main__':

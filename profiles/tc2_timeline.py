@@ -1,5 +1,5 @@
 """Timeline of CTA 0 of the tensor-core conditioner (developer instrumentation):
-python profiles/tc2_timeline.py CIN COUT HW B [dbg] [fused: checker|channel]"""
+python profiles/tc2_timeline.py CIN COUT HW B [dbg] [fused: checker|channel|none] [extra kernel flags, e.g. 0x10000 = 3xTF32]"""
 import ctypes
 import os
 import sys
@@ -13,7 +13,8 @@ import nfb200._lib as L  # noqa: E402
 torch.set_grad_enabled(False)
 cin, cout, hw, B = (int(a) for a in sys.argv[1:5])
 dbg = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-fused = sys.argv[6] if len(sys.argv) > 6 else None
+fused = sys.argv[6] if len(sys.argv) > 6 and sys.argv[6] != 'none' else None
+extra = int(sys.argv[7], 0) if len(sys.argv) > 7 else 0
 if fused:
     dims = (cin // 2, 2 * hw, 2 * hw) if fused == 'checker' else (2 * cin, hw, hw)
     cpl = nfb200.flows.AffineCoupling(dims, masking='checkerboard' if fused == 'checker' else 'channelwise').to('cuda:0').eval()
@@ -39,14 +40,13 @@ buf = torch.zeros(4 * 512, dtype=torch.int64, device='cuda:0')
 fn = L.lib().nfb_debug_timeline
 fn.argtypes = [ctypes.c_void_p]
 fn(buf.data_ptr())
-net.kernel_flags = L.conv_debug(dbg)
+net.kernel_flags = L.conv_debug(dbg) | extra
 run()
 torch.cuda.synchronize()
 fn(None)
 ev = buf.cpu().view(4, 512)
-NAMES = {1: 'mma wait w_full', 2: 'mma got w_full', 10: 'mma wait act0', 11: 'mma wait act1', 12: 'mma wait act2', 13: 'mma wait act3',
-         14: 'mma got act0', 15: 'mma got act1', 16: 'mma got act2', 17: 'mma got act3',
-         28: 'commit acc0', 29: 'commit acc1', 30: 'commit war0 / epi wait acc', 22: 'commit w_empty0', 23: 'commit w_empty1',
+NAMES = {1: 'mma wait w_full', 2: 'mma got w_full', 10: 'mma wait act0', 11: 'mma wait act1', 12: 'mma got act0', 13: 'mma got act1',
+         26: 'commit acc0', 27: 'commit acc1', 28: 'commit war0', 30: 'epi wait acc', 22: 'commit w_empty0', 23: 'commit w_empty1',
          31: 'epi got acc', 32: 'epi wait war', 33: 'epi got war', 34: 'epi signal..', 35: 'epi signalled',
          36: 'epi acc loaded', 0: 'kernel entry', 1: 'prologue done', 50: 'kernel exit', 40: 'epi unit start', 41: 'epi out layer', 42: 'epi done'}
 rows = []

@@ -579,9 +579,12 @@ def test_convnet_variants_agree(key, values, cin, cout, hw):
 
 @pytest.mark.parametrize('cin,cout,hw,B', [(6, 12, 16, 3), (24, 48, 8, 5), (96, 192, 4, 7), (6, 12, 16, 256),
                                            (40, 70, 8, 2), (24, 48, 8, 256), (96, 192, 4, 256)])
-def test_convnet_tensor_core_path(cin, cout, hw, B):
-    """tcgen05 3xTF32 implicit-GEMM conditioner vs the FP32-FFMA kernel and the CPU oracle (same tolerance class)."""
+@pytest.mark.parametrize('operands', ['f16split', 'tf32x3'])
+def test_convnet_tensor_core_path(cin, cout, hw, B, operands):
+    """tcgen05 implicit-GEMM conditioner (default FP16-split operands; 3xTF32 with NFB_CONV_TF32) vs the FP32-FFMA kernel and
+    the CPU oracle (same tolerance class)."""
     import nfb200._lib as L
+    fmt = L.CONV_TF32 if operands == 'tf32x3' else 0
     F = nfb().flows
     torch.manual_seed(cin + hw)
     net = F.ConvNet(cin, cout)
@@ -595,10 +598,13 @@ def test_convnet_tensor_core_path(cin, cout, hw, B):
     net.to(DEV)
     net.kernel_flags = L.CONV_FFMA
     ffma = net(x.to(DEV))
-    net.kernel_flags = 0
+    net.kernel_flags = fmt
     tc = net(x.to(DEV))
+    net.kernel_flags = fmt | L.CONV_PAIR
+    tc_pair = net(x.to(DEV))
     torch.cuda.synchronize()
     scale = max(1.0, float(ref.abs().max()))
+    close(tc_pair, tc, rtol=2e-6, atol=1e-6 * scale, what='paired tiles vs single tile')
     e_tc = float((tc[:8].cpu().double() - ref64).abs().max())
     e_ff = float((ffma[:8].cpu().double() - ref64).abs().max())
     e_ref = float((ref.double() - ref64).abs().max())
@@ -660,6 +666,45 @@ def test_fused_conditioner_coupling(dims, masking, odd, B):
     scale = max(1.0, float(z3.abs().max()))
     close(z1, z3, rtol=2e-5, atol=4e-6 * scale, what='tensor-core vs ffma conditioner')
     close(l1, l3, rtol=2e-5, atol=4e-6 * max(1.0, float(l3.abs().max())), what='ldj tensor-core vs ffma')
+    # 3xTF32 operands (NFB_CONV_TF32): fused and two-kernel paths bit-identical again, and within rounding of the default
+    cpl.net.kernel_flags = L.CONV_TF32
+    z6, l6 = cpl(x, l0.clone())
+    cpl.fused_conditioner = True
+    z7, l7 = cpl(x, l0.clone())
+    assert torch.equal(z6, z7)
+    close(z7, z3, rtol=2e-5, atol=4e-6 * scale, what='3xTF32 vs ffma conditioner')
+    close(l7, l3, rtol=2e-5, atol=4e-6 * max(1.0, float(l3.abs().max())), what='ldj 3xTF32 vs ffma')
+
+
+@pytest.mark.parametrize('hw', [16, 8, 4])
+def test_fp16_split_range(hw):
+    """The default operand format of the tensor-core conditioner represents x as fp16 hi + 2^-10 fp16 lo: tiny inputs (hi is a
+    subnormal or zero) keep full precision through lo; an input beyond the fp16 range cannot be represented and must come
+    back as NaN for that sample (never a finite wrong number), while NFB_CONV_TF32 and the FFMA kernel handle it."""
+    import nfb200._lib as L
+    F = nfb().flows
+    torch.manual_seed(hw)
+    net = F.ConvNet(6, 12)
+    perturb_(net, 4)
+    net.eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(9, 6, hw, hw)
+    x[1] *= 1e-6          # far below the fp16 normal range
+    x[2] *= 3e4           # |x| up to ~1e5: beyond 65504
+    x[2, 0, 0, 0] = 7e4
+    with torch.no_grad():
+        ref64 = O.resnet_conditioner(O.to_dtype(sd, torch.float64), '', x.double())
+    net.to(DEV)
+    out = net(x.to(DEV)).cpu()
+    ok = [0, 1, 3, 4, 5, 6, 7, 8]
+    sc = float(ref64[ok].abs().max())
+    assert torch.isfinite(out[ok]).all()
+    close(out[ok], ref64[ok].float(), rtol=2e-5, atol=4e-6 * sc, what='fp16 split incl. tiny inputs')
+    assert torch.isnan(out[2]).any() and not torch.isinf(out[2]).any()
+    for flags in (L.CONV_TF32, L.CONV_FFMA):
+        net.kernel_flags = flags
+        o2 = net(x.to(DEV)).cpu()
+        close(o2[2], ref64[2].float(), rtol=2e-5, atol=4e-6 * float(ref64[2].abs().max()), what='large inputs, flags %#x' % flags)
 
 
 @pytest.mark.parametrize('dims,masking', [((3, 32, 32), 'checkerboard'), ((12, 16, 16), 'channelwise'),
