@@ -220,6 +220,7 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
 #define NFB_CONV_TF32 0x10000 /* tensor-core kernel with 3xTF32 operands instead of the default FP16 split */
+#define NFB_CONV_SINGLE 0x20000 /* 16x16 maps: one sample per CTA at a time even when the batch would allow two in flight */
 #define NFB_CONV_PAIR 0x80
 #define NFB_CONV_GROUPS_SHIFT 4
 #define NFB_CONV_GROUPS(g) ((g) << NFB_CONV_GROUPS_SHIFT)

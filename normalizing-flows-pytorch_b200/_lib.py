@@ -18,6 +18,7 @@ SPLIT_1D, SPLIT_CHECKER, SPLIT_CHANNEL = 0, 1, 2
 CONV_FFMA = 0x8
 CONV_PAIR = 0x80
 CONV_TF32 = 0x10000
+CONV_SINGLE = 0x20000
 
 
 def conv_variant(v):

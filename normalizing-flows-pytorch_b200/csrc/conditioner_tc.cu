@@ -337,7 +337,12 @@ constexpr int kTileCols = 256;            // TMEM columns reserved per tile
 // two tiles of a 16x16 sample (epilogue of one under the MMAs of the other, weights streamed once for both): ~1.5x the
 // work per SM-second of the single-tile unit, which leaves the tensor core idle during every epilogue, at the price of
 // half as many CTAs -- the choice when the batch (or several batches in flight) fills the machine anyway.
-template <int H, int W, bool PAIR, bool F16 = false>
+// DUAL (16x16 maps, FP16 split): TWO units (samples) are in flight per CTA -- separate activation planes and accumulators,
+// one shared weight ring.  The MMA lane issues [A tile 0, A tile 1, B tile 0, B tile 1] per layer, each epilogue warp quad
+// serves "its" tile of A and then of B, so the tensor pipe always has the other sample's layer to run while one sample is
+// in its epilogue, and the serial head and tail of a sample (gather, input layer, output layer, coupling) hide behind the
+// other sample's 3x3 layers.  The residual stream of the 4 tiles lives in shared memory instead of registers.
+template <int H, int W, bool PAIR, bool F16 = false, bool DUAL = false>
 struct TcGeom {
     static constexpr int HW = H * W;
     static constexpr bool LINKED = HW > 128 || PAIR;    // two tiles per unit, ping-pong (16x16: the two halves of a sample)
@@ -352,7 +357,11 @@ struct TcGeom {
     static constexpr int NPL = F16 ? 4 : 8;             // planes of 16 B per position: 4 TF32 / 8 FP16 channels each
     static constexpr int NJ = F16 ? 2 : 4;              // k-steps per tap of a 32-channel layer
     static constexpr int ACT_BYTES = 2 * NPL * PS;      // hi planes + lo planes
-    static_assert(T <= 2 && T * kTileCols <= 512, "unit exceeds TMEM");
+    static constexpr int NU = DUAL ? 2 : 1;             // units in flight per CTA
+    static constexpr int TC = DUAL ? 128 : kTileCols;   // TMEM columns per tile (DUAL: 2 accumulator groups, out layer <= 128)
+    static constexpr int XS_BYTES = DUAL ? NU * T * 32 * 128 * 4 : 0;  // residual stream [unit][tile][channel][row]
+    static_assert(T <= 2 && NU * T * TC <= 512, "units exceed TMEM");
+    static_assert(!DUAL || (HW == 256 && F16 && !PAIR), "DUAL: 16x16 maps with FP16-split operands");
     static_assert(HW == 256 || 128 % HW == 0, "tile must hold whole samples");
     static_assert(!(PAIR && HW > 128), "PAIR is for maps of at most 128 pixels");
 };
@@ -371,31 +380,36 @@ struct PostOp {
     const float* log_s;         // (C)
 };
 
-template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP, bool F16>
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP, bool F16, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
                   int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, PostOp post, int G, int dbg) {
-    using GM = TcGeom<H, W, PAIR, F16>;
+    using GM = TcGeom<H, W, PAIR, F16, DUAL>;
     constexpr int HW = GM::HW, T = GM::T, SPT = GM::SPT, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD,
-                  PB = GM::PB, PS = GM::PS, NPL = GM::NPL, NJ = GM::NJ;
+                  PB = GM::PB, PS = GM::PS, NPL = GM::NPL, NJ = GM::NJ, NU = GM::NU, TC = GM::TC;
     constexpr bool LINKED = GM::LINKED;
     constexpr int SLOT = slot_bytes(F16);
+    static_assert(!DUAL || CP == 0, "the next-step post-op has no two-unit variant");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* act = smem_raw;                              // [2 NPL planes][PB][16 B]
-    unsigned char* ring = smem_raw + GM::ACT_BYTES;             // 2 x SLOT
-    float* cst = reinterpret_cast<float*>(ring + 2 * SLOT);
+    unsigned char* act = smem_raw;                              // [NU units][2 NPL planes][PB][16 B]
+    unsigned char* ring = smem_raw + NU * GM::ACT_BYTES;        // 2 x SLOT
+    float* xs = reinterpret_cast<float*>(ring + 2 * SLOT);      // DUAL: residual stream [unit][tile][32 channels][128 rows]
+    float* cst = reinterpret_cast<float*>(ring + 2 * SLOT + GM::XS_BYTES);
 
     const TcPlan P = tc_plan(Cin, Cout, F16 ? 1 : 0);
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     uint64_t* bars = reinterpret_cast<uint64_t*>(cst + ((n_cst + 3) & ~3));
     // barrier indices
-    constexpr int W_FULL = 0, W_EMPTY = 2, ACT_READY = 4, ACC_DONE = 6, WAR0 = 8, N_BARS = 9;
+    // ([unit][tile] for ACT_READY / ACC_DONE; an odd count keeps the 16-byte alignment of the tables behind the barriers)
+    constexpr int W_FULL = 0, W_EMPTY = 2, ACT_READY = 4, ACC_DONE = 4 + 2 * NU, WAR0 = 4 + 4 * NU, N_BARS = (4 + 5 * NU) | 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [8 warps][2]
     uint4* mask_tab = reinterpret_cast<uint4*>(red + 16);        // [T][9 taps]: rows of the tile whose tap leaves the image
-    uint4* prog = mask_tab + 2 * 9;                              // [T][9 taps in issue order][mask, 4 k-steps]: see below
-    // (+ one spare table row: the issue loop reads one tap ahead); CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
-    float* wpost = reinterpret_cast<float*>(prog + (2 * 9 + 1) * 5);
+    constexpr int ROWW = 1 + NJ;                                 // uint4 per row of the issue program
+    constexpr int N_ROWS = 2 * NU * T * 9;                       // [weight slot][unit][tile][tap in issue order]
+    uint4* prog = mask_tab + 2 * 9;                              // N_ROWS x [lane mask, NJ k-steps]: see below
+    // CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
+    float* wpost = reinterpret_cast<float*>(prog + N_ROWS * ROWW);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
 
@@ -408,41 +422,19 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     const int qps = SLOT / out_chunk_bytes;                     // out chunks per weight stage
     const int n_out_stage = (nq + qps - 1) / qps;
     const int n_stage = P.n_in + 4 + n_out_stage;
-    const int n_units = (B + SPU - 1) / SPU;
+    const int n_units = ((B + SPU - 1) / SPU + NU - 1) / NU;    // loop iterations: NU units each
 
     // ---- prologue: barriers, constants, TMEM ----------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(bar(W_FULL), 1); mbar_init(bar(W_FULL + 1), 1);
         mbar_init(bar(W_EMPTY), 1); mbar_init(bar(W_EMPTY + 1), 1);
-        mbar_init(bar(ACT_READY), 128 * CS); mbar_init(bar(ACT_READY + 1), 128 * CS);
-        mbar_init(bar(ACC_DONE), 1); mbar_init(bar(ACC_DONE + 1), 1);
-        mbar_init(bar(WAR0), 1);
+        for (int i = 0; i < 2 * NU; ++i) { mbar_init(bar(ACT_READY + i), 128 * CS); mbar_init(bar(ACC_DONE + i), 1); }
+        for (int i = 0; i < NU; ++i) mbar_init(bar(WAR0 + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < T * 9 * 4) {
         const int t = tid / 36, tap = (tid % 36) / 4, wd = tid % 4;
         reinterpret_cast<uint32_t*>(mask_tab)[tid] = edge_mask<H, W>(t, tap / 3 - 1, tap % 3 - 1, wd);
-    }
-    // Issue program of a 32->32 3x3 layer (4 k-steps per tap): the operands of all 72 k-steps are the same in every such
-    // layer, so they are tabulated once: per tap [lane mask | 4 x (A_hi descriptor lo word, A_lo descriptor lo word, B
-    // offset inside the weight slot, TMEM column | accumulate << 31)] in the order the MMA lane issues them.
-    if (tid < T * 36 && (tid % 4) < NJ) {
-        const int t = tid / 36, i = (tid % 36) / 4, j = tid % 4;
-        const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
-        const int tap = static_cast<int>((order >> (4 * i)) & 15u);
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const int Ge = G < NJ ? G : NJ;
-        const int kc = NJ * i + j;
-        const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128 + dy * W + dx);
-        uint4 e;
-        e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-        e.y = (((smem_u32(act + NPL * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-        e.z = static_cast<uint32_t>((tap * NJ + j) * 128);
-        e.w = static_cast<uint32_t>(t * kTileCols + (kc % Ge) * 64) | (kc >= Ge ? 0x80000000u : 0u);
-        prog[(t * 9 + i) * 5 + 1 + j] = e;
-        if (j == 0)
-            prog[(t * 9 + i) * 5] = make_uint4(edge_mask<H, W>(t, dy, dx, 0), edge_mask<H, W>(t, dy, dx, 1),
-                                               edge_mask<H, W>(t, dy, dx, 2), edge_mask<H, W>(t, dy, dx, 3));
     }
     if (CP > 0) {
         for (int i = tid; i < CP * CP; i += kThreads) {
@@ -516,17 +508,46 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         // uniform registers and emits back-to-back UTCHMMA.  (Measured: `if (lane == 0)` or a predicated asm wraps every
         // MMA in an ELECT loop with R2UR moves, ~200 cycles per k-step; fully unrolled issue code is instruction-fetch
         // bound, ~380 cycles per k-step.)
+        // Issue program of a 32->32 3x3 layer: the operands of its k-steps are the same in every such layer, so the complete
+        // low words of the three descriptors and the accumulator address are tabulated once per (weight slot, unit, tile,
+        // tap in issue order): [lane mask | NJ x (A_hi descriptor, A_lo descriptor, B descriptor, TMEM address)].  The issuing
+        // lane is a single thread whose instructions cost their full latency (~5 cycles each, measured): with these rows a
+        // tap is 1 + NJ shared-memory loads, the register -> uniform-register moves and its MMAs, nothing else.
+        {
+            const int Ge = G < NJ ? G : NJ;
+            for (int r = lane; r < N_ROWS; r += 32) {
+                const int i = r % 9, t = (r / 9) % T, u = (r / (9 * T)) % NU, slot = r / (9 * T * NU);
+                const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
+                const int tap = static_cast<int>((order >> (4 * i)) & 15u);
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                prog[r * ROWW] = make_uint4(edge_mask<H, W>(t, dy, dx, 0), edge_mask<H, W>(t, dy, dx, 1),
+                                            edge_mask<H, W>(t, dy, dx, 2), edge_mask<H, W>(t, dy, dx, 3));
+                for (int j = 0; j < NJ; ++j) {
+                    const int kc = NJ * i + j;
+                    const uint32_t a_off = static_cast<uint32_t>(u * (GM::ACT_BYTES >> 4) + 2 * j * PB + GUARD + t * 128 + dy * W + dx);
+                    uint4 e;
+                    e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+                    e.y = (((smem_u32(act + NPL * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+                    e.z = (((smem_u32(ring + slot * SLOT) >> 4) + static_cast<uint32_t>((tap * NJ + j) * 128)) & 0x3FFFu) | ((1024u >> 4) << 16);
+                    e.w = tmem + static_cast<uint32_t>(u * T * TC + t * TC + (kc % Ge) * 64);
+                    prog[r * ROWW + 1 + j] = e;
+                }
+            }
+            __syncwarp();
+        }
         if (elect_one()) {
             const uint64_t dAH = make_smem_desc(smem_u32(act), PS, 128);
             const uint64_t dAL = make_smem_desc(smem_u32(act + NPL * PS), PS, 128);
             const bool no_mma = (dbg & 1) != 0, no_lo = (dbg & 4) != 0;
-            uint32_t cnt = 0, ph_act0 = 0, ph_act1 = 0;
+            uint32_t cnt = 0;
+            uint32_t ph_act = 0;  // bit (2u + t): phase of ACT_READY[u][t]
             Timeline tl;
             tl.init(2, blockIdx.x == 0);
-            auto wait_act = [&](int t) {
+            auto wait_act = [&](int u, int t) {
                 tl.stamp(10 + t);
-                if (t == 0) { mbar_wait(bar(ACT_READY), ph_act0, 10); ph_act0 ^= 1u; }
-                else { mbar_wait(bar(ACT_READY + 1), ph_act1, 11); ph_act1 ^= 1u; }
+                const int i = 2 * u + t;
+                mbar_wait(bar(ACT_READY + i), (ph_act >> i) & 1u, 10 + i);
+                ph_act ^= 1u << i;
                 tc_fence_after();
                 tl.stamp(12 + t);
             };
@@ -548,6 +569,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         const int Ge = G < nj ? G : nj;
                         const uint64_t dB = make_smem_desc(wbase, 1024, 128);
                         int kc = 0, rr = 0;  // k-steps issued into this tile's accumulators; round-robin group
+                        uint32_t uA = 0, uT = 0;  // current unit: offset of its activation planes (16-byte units) / TMEM columns
+                        int cur_u = 0;
                         // one k-step = 8 input channels of one tap: [main | comp] += a_hi * [w_hi | w_lo]; comp += a_lo * w_hi
                         auto kstep = [&](uint32_t tbase, uint64_t a_hi, uint64_t a_lo, uint64_t b, const uint4& m) {
                             const uint32_t d = tbase + static_cast<uint32_t>(rr * 64);
@@ -560,68 +583,64 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         };
                         // taps order[i_lo .. i_hi) of tile t
                         auto issue = [&](int t, uint64_t order, int i_lo, int i_hi) {
-                            if (nj == NJ) {
-                                // tabulated operands: 5 shared-memory loads feed 8 MMAs
-                                const uint32_t a_hi32 = (128u >> 4) | (1u << 14);
-                                const uint32_t b_hi32 = (128u >> 4) | (1u << 14);
-                                const uint32_t b_lo32 = ((wbase >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);
-                                const uint4* pt = prog + (t * 9 + i_lo) * 5;
-                                // software pipeline: the table entries of tap i + 1 are loaded before the MMAs of tap i are issued
-                                // (a single thread, `asm volatile` MMAs: nothing else hides the shared-memory latency; measured
-                                // ~140 cycles per tap without it)
-                                uint4 m = pt[0];
-                                uint4 e[NJ];
+                            if (nj == NJ && !no_lo) {
+                                // tabulated operands (see the prologue of this warp)
+                                if (no_mma) return;
+                                constexpr uint32_t hi32 = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+                                const uint4* pt = prog + (((slot * NU + cur_u) * T + t) * 9 + i_lo) * ROWW;
+                                auto tap_row = [&](const uint4* row, bool first) {
+                                    const uint4 m = row[0];
+                                    uint4 e[NJ];
 #pragma unroll
-                                for (int j = 0; j < NJ; ++j) e[j] = pt[1 + j];
-#pragma unroll 1
-                                for (int i = i_lo; i < i_hi; ++i) {
-                                    pt += 5;  // the table has one spare row after the last tap of a tile (the next tile's / padding)
-                                    const uint4 m_n = pt[0];
-                                    uint4 e_n[NJ];
+                                    for (int j = 0; j < NJ; ++j) e[j] = row[1 + j];
 #pragma unroll
-                                    for (int j = 0; j < NJ; ++j) e_n[j] = pt[1 + j];
-                                    if (!no_mma) {
-#pragma unroll
-                                        for (int j = 0; j < NJ; ++j) {
-                                            const uint64_t b = (static_cast<uint64_t>(b_hi32) << 32) | (b_lo32 + e[j].z);
-                                            const uint32_t d = tmem + (e[j].w & 0xFFFFu);
-                                            mma_any<F16>(d, (static_cast<uint64_t>(a_hi32) << 32) | e[j].x, b, idesc_n<F16>(64), e[j].w >> 31, m.x, m.y, m.z, m.w);
-                                            if (!no_lo)
-                                                mma_any<F16>(d + 32, (static_cast<uint64_t>(a_hi32) << 32) | e[j].y, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
-                                        }
+                                    for (int j = 0; j < NJ; ++j) {
+                                        const uint64_t b = (static_cast<uint64_t>(hi32) << 32) | e[j].z;
+                                        // the centre tap comes first: its first Ge k-steps start the accumulator groups
+                                        const uint32_t acc = (first && j < Ge) ? 0u : 1u;
+                                        mma_any<F16>(e[j].w, (static_cast<uint64_t>(hi32) << 32) | e[j].x, b, idesc_n<F16>(64), acc, m.x, m.y, m.z, m.w);
+                                        mma_any<F16>(e[j].w + 32, (static_cast<uint64_t>(hi32) << 32) | e[j].y, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
                                     }
-                                    m = m_n;
-#pragma unroll
-                                    for (int j = 0; j < NJ; ++j) e[j] = e_n[j];
-                                }
+                                };
+                                int i = i_lo;
+                                if (i == 0) { tap_row(pt, true); ++i; pt += ROWW; }
+#pragma unroll 1
+                                for (; i < i_hi; ++i, pt += ROWW) tap_row(pt, false);
                                 return;
                             }
-                            const uint32_t tbase = tmem + static_cast<uint32_t>(t * kTileCols);
+                            const uint32_t tbase = tmem + uT + static_cast<uint32_t>(t * TC);
 #pragma unroll 1
                             for (int i = i_lo; i < i_hi; ++i) {
                                 const int tap = static_cast<int>((order >> (4 * i)) & 15u);
                                 const int ty = (tap * 11) >> 5, dy = ty - 1, dx = tap - 3 * ty - 1;
                                 const uint4 m = mask_tab[t * 9 + tap];
-                                const uint32_t a_off = static_cast<uint32_t>(GUARD + t * 128 + dy * W + dx);
+                                const uint32_t a_off = uA + static_cast<uint32_t>(GUARD + t * 128 + dy * W + dx);
                                 const uint64_t a_hi = dAH + a_off, a_lo = dAL + a_off, b = dB + static_cast<uint32_t>(tap * nj * 128);
 #pragma unroll 1
                                 for (int j = 0; j < nj; ++j) kstep(tbase, a_hi + 2 * j * PB, a_lo + 2 * j * PB, b + j * 128, m);
                             }
                         };
-                        wait_act(0);
-                        if (LINKED) {
-                            issue(0, kOrder0, 0, 6);
-                            wait_act(1);
-                            issue(0, kOrder0, 6, 9);
-                            commit(ACC_DONE);
+#pragma unroll 1
+                        for (int u = 0; u < NU; ++u) {
+                            uA = static_cast<uint32_t>(u * (GM::ACT_BYTES >> 4));
+                            uT = static_cast<uint32_t>(u * T * TC);
+                            cur_u = u;
                             kc = 0; rr = 0;
-                            issue(1, kOrder1, 0, 4);
-                            commit(WAR0);  // tile 0's rows are no longer read: its epilogue may overwrite them
-                            issue(1, kOrder1, 4, 9);
-                            commit(ACC_DONE + 1);
-                        } else {
-                            issue(0, kOrder0, 0, 9);
-                            commit(ACC_DONE);
+                            wait_act(u, 0);
+                            if (LINKED) {
+                                issue(0, kOrder0, 0, 6);
+                                wait_act(u, 1);
+                                issue(0, kOrder0, 6, 9);
+                                commit(ACC_DONE + 2 * u);
+                                kc = 0; rr = 0;
+                                issue(1, kOrder1, 0, 4);
+                                commit(WAR0 + u);  // tile 0's rows are no longer read: its epilogue may overwrite them
+                                issue(1, kOrder1, 4, 9);
+                                commit(ACC_DONE + 2 * u + 1);
+                            } else {
+                                issue(0, kOrder0, 0, 9);
+                                commit(ACC_DONE + 2 * u);
+                            }
                         }
                     } else {
                         // ---- 1x1 output layer, chunks of NW columns: [main NW | comp NW] ----
@@ -633,19 +652,20 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                             const uint64_t dB = make_smem_desc(wbase + static_cast<uint32_t>(qi * out_chunk_bytes),
                                                                static_cast<uint32_t>(2 * NW * 16), 128);
 #pragma unroll 1
-                            for (int t = 0; t < T; ++t) {
-                                wait_act(t);
-                                const uint32_t d = tmem + static_cast<uint32_t>(t * kTileCols);
+                            for (int ut = 0; ut < NU * T; ++ut) {
+                                const int u = ut / T, t = ut % T;
+                                wait_act(u, t);
+                                const uint32_t d = tmem + static_cast<uint32_t>(u * T * TC + t * TC);
 #pragma unroll
                                 for (int j = 0; j < NJ; ++j) {
-                                    const uint32_t a_off = static_cast<uint32_t>(2 * j * PB + GUARD + t * 128);
+                                    const uint32_t a_off = static_cast<uint32_t>(u * (GM::ACT_BYTES >> 4) + 2 * j * PB + GUARD + t * 128);
                                     const uint32_t b_off = static_cast<uint32_t>(j * 4 * NW);  // 2 blocks of 2NW rows x 16 B
                                     if (!no_mma) {
                                         mma_any<F16>(d, dAH + a_off, dB + b_off, i_main, j > 0 ? 1u : 0u, 0u, 0u, 0u, 0u);
                                         if (!no_lo) mma_any<F16>(d + NW, dAL + a_off, dB + b_off, i_comp, 1u, 0u, 0u, 0u, 0u);
                                     }
                                 }
-                                commit(ACC_DONE + t);
+                                commit(ACC_DONE + 2 * u + t);
                             }
                         }
                     }
@@ -662,25 +682,53 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         const int pos = tile * 128 + row;                // position inside the unit
         const int pix = HW > 128 ? pos : row % HW;
         const int yy = pix / W, xx = pix % W;
-        const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(tile * kTileCols);
-        const uint32_t b_acc = bar(ACC_DONE + tile), b_act = bar(ACT_READY + tile);
-        unsigned char* my_act = act + (GUARD + pos) * 16;
-        uint32_t ph_acc = 0, ph_war = 0;
+        const uint32_t t_lane0 = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(tile * TC);
+        unsigned char* my_act0 = act + (GUARD + pos) * 16;
+        uint32_t ph_acc = 0, ph_war = 0;  // bit u: phase of ACC_DONE[u][tile] / WAR0[u]
         Timeline tl;
         tl.init(grp, blockIdx.x == 0 && (tid & 127) == 0);
 
+        // ---- the unit this thread is working on (DUAL: the stages below alternate between the two units in flight) --------
+        int cu = 0, unit = 0, b = 0;
+        bool valid = false;
+        const float* zb = zsrc;
+        uint32_t t_lane = t_lane0, b_acc = bar(ACC_DONE + tile), b_act = bar(ACT_READY + tile), b_war = bar(WAR0);
+        unsigned char* my_act = my_act0;
+        float* xs_u = xs;  // DUAL: this thread's column of the residual stream, [channel][128 rows]
+        // FP16 split: largest |activation| this thread has converted for the unit.  At >= 65504 the conversion saturates and
+        // the sums that consumed it are wrong: the thread then returns NaN for its outputs of that unit (a loud failure; such
+        // data needs NFB_CONV_TF32), see the output layer.
+        float amax = 0.f, amax_u0 = 0.f, amax_u1 = 0.f;
+        auto set_unit = [&](int u) {
+            cu = u;
+            const int un = unit * NU + u;
+            b = HW > 128 ? un : un * SPU + tile * SPT + row / HW;
+            valid = b < B;
+            zb = zsrc + static_cast<size_t>(b) * (MODE < 0 ? static_cast<size_t>(Cin) * HW : static_cast<size_t>(g.D));
+            t_lane = t_lane0 + static_cast<uint32_t>(u * T * TC);
+            my_act = my_act0 + u * GM::ACT_BYTES;
+            b_acc = bar(ACC_DONE + 2 * u + tile);
+            b_act = bar(ACT_READY + 2 * u + tile);
+            b_war = bar(WAR0 + u);
+            if (DUAL) xs_u = xs + ((u * T + tile) * 32) * 128 + row;
+            amax = u ? amax_u1 : amax_u0;
+        };
+        auto end_unit = [&]() {
+            if (cu) amax_u1 = amax;
+            else amax_u0 = amax;
+        };
         auto wait_acc = [&]() {
             tl.stamp(30);
-            mbar_wait(b_acc, ph_acc, 30);
-            ph_acc ^= 1u;
+            mbar_wait(b_acc, (ph_acc >> cu) & 1u, 30 + cu);
+            ph_acc ^= 1u << cu;
             tc_fence_after();
             tl.stamp(31);
         };
         auto wait_war = [&]() {
             if (LINKED && grp == 0) {
                 tl.stamp(32);
-                mbar_wait(bar(WAR0), ph_war, 31);
-                ph_war ^= 1u;
+                mbar_wait(b_war, (ph_war >> cu) & 1u, 32 + cu);
+                ph_war ^= 1u << cu;
                 tl.stamp(33);
             }
         };
@@ -716,10 +764,6 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             }
             tl.stamp(36);
         };
-        // FP16 split: largest |activation| this thread has converted for the current unit.  At >= 65504 the conversion
-        // saturates and the sums that consumed it are wrong: the thread then returns NaN for its outputs (a loud failure;
-        // such data needs NFB_CONV_TF32), see the output layer.
-        float amax = 0.f;
         // a[EC] (activated) -> hi / lo planes of this thread's position
         auto store_act = [&](int sub, const float (&a)[EC]) {
             if (dbg & 16) return;  // profiling knob: no activation stores
@@ -748,6 +792,20 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             }
         };
 
+        // residual stream of this thread's position: registers, or (DUAL) shared memory
+        float xres[DUAL ? 1 : NCH];
+        auto xr_load = [&](int sub, float (&x)[EC]) {
+#pragma unroll
+            for (int i = 0; i < EC; ++i) x[i] = DUAL ? xs_u[(ch0 + sub * EC + i) * 128] : xres[DUAL ? 0 : sub * EC + i];
+        };
+        auto xr_store = [&](int sub, const float (&x)[EC]) {
+#pragma unroll
+            for (int i = 0; i < EC; ++i) {
+                if (DUAL) xs_u[(ch0 + sub * EC + i) * 128] = x[i];
+                else xres[DUAL ? 0 : sub * EC + i] = x[i];
+            }
+        };
+
         const float* c_b0 = cst;
         auto c_blk = [&](int blk, int k) { return cst + 32 + blk * 128 + k * 32; };
         const float* c_sO = cst + 288;
@@ -756,19 +814,18 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         float sa = 0.f, sb = 0.f;
         if (FUSED) { sa = __ldg(p_sa); sb = __ldg(p_sb); }
 
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             tl.stamp(40);
-            const int b = HW > 128 ? unit : unit * SPU + tile * SPT + row / HW;
-            const bool valid = b < B;
-            amax = 0.f;
-            const float* zb = zsrc + static_cast<size_t>(b) * (MODE < 0 ? static_cast<size_t>(Cin) * HW : static_cast<size_t>(g.D));
-            float xres[NCH];
+            amax_u0 = amax_u1 = 0.f;
 
-            // ---- in conv: Cin -> 32 in passes of <= 32 input channels; the partial sums meet in registers ------------
+            // ---- in conv: Cin -> 32 in passes of <= 32 input channels; the partial sums meet in the residual stream ----
 #pragma unroll 1
             for (int c = 0; c < P.n_in; ++c) {
                 const int CI = (Cin - c * kF) < kF ? (Cin - c * kF) : kF;
                 const int n4 = F16 ? ((CI + 15) & ~15) / 4 : ((CI + 7) & ~7) / 4;
+#pragma unroll 1
+                for (int u = 0; u < NU; ++u) {
+                set_unit(u);
                 // this thread's share of the chunk: all loads first (they are independent: one round trip to L2), then the
                 // hi/lo split and the stores
                 constexpr int NG = 8 / CS;  // channel groups of 4 per thread
@@ -808,37 +865,54 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     }
                 }
                 signal_act();
+                end_unit();
+                }
+#pragma unroll 1
+                for (int u = 0; u < NU; ++u) {
+                set_unit(u);
                 wait_acc();
                 const int nj = (c == P.n_in - 1) ? P.nj_last : NJ;
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
                     float v[EC];
                     load_acc(G < nj ? G : nj, sub, v);
-                    if (c == 0) {
+                    if (c > 0) {
+                        float x[EC];
+                        xr_load(sub, x);
 #pragma unroll
-                        for (int i = 0; i < EC; ++i) xres[sub * EC + i] = v[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < EC; ++i) xres[sub * EC + i] += v[i];
+                        for (int i = 0; i < EC; ++i) v[i] += x[i];
                     }
+                    xr_store(sub, v);
                 }
                 wait_war();
+                end_unit();
+                }
             }
+#pragma unroll 1
+            for (int u = 0; u < NU; ++u) {
+            set_unit(u);
 #pragma unroll
             for (int sub = 0; sub < NP; ++sub) {
-                float a[EC];
+                float a[EC], x[EC];
+                xr_load(sub, x);
 #pragma unroll
                 for (int i = 0; i < EC; ++i) {
                     const int ch = ch0 + sub * EC + i;
-                    xres[sub * EC + i] += c_b0[ch];
-                    a[i] = fmaxf(fmaf(xres[sub * EC + i], c_blk(0, 0)[ch], c_blk(0, 1)[ch]), 0.f);
+                    x[i] += c_b0[ch];
+                    a[i] = fmaxf(fmaf(x[i], c_blk(0, 0)[ch], c_blk(0, 1)[ch]), 0.f);
                 }
+                xr_store(sub, x);
                 store_act(sub, a);
             }
             signal_act();
+            end_unit();
+            }
             // ---- two residual blocks ---------------------------------------------------------------------------------
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll 1
+                for (int u = 0; u < NU; ++u) {
+                set_unit(u);
                 wait_acc();
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
@@ -850,26 +924,38 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     store_act(sub, a);
                 }
                 signal_act();
-                wait_acc();
+                end_unit();
+                }
                 const float* sN = blk == 0 ? c_blk(1, 0) : c_sO;  // the BatchNorm that consumes the updated stream
                 const float* tN = blk == 0 ? c_blk(1, 1) : c_tO;
+#pragma unroll 1
+                for (int u = 0; u < NU; ++u) {
+                set_unit(u);
+                wait_acc();
 #pragma unroll
                 for (int sub = 0; sub < NP; ++sub) {
-                    float v[EC], a[EC];
+                    float v[EC], a[EC], x[EC];
                     load_acc(G < NJ ? G : NJ, sub, v);  // conv2 + skip
+                    xr_load(sub, x);
 #pragma unroll
                     for (int i = 0; i < EC; ++i) {
                         const int ch = ch0 + sub * EC + i;
-                        xres[sub * EC + i] += v[i] + c_blk(blk, 3)[ch];
-                        a[i] = fmaxf(fmaf(xres[sub * EC + i], sN[ch], tN[ch]), 0.f);
+                        x[i] += v[i] + c_blk(blk, 3)[ch];
+                        a[i] = fmaxf(fmaf(x[i], sN[ch], tN[ch]), 0.f);
                     }
+                    xr_store(sub, x);
                     if (sub == 0) wait_war();
                     store_act(sub, a);
                 }
                 signal_act();
+                end_unit();
+                }
             }
             // ---- output layer ----------------------------------------------------------------------------------------
             tl.stamp(41);
+#pragma unroll 1
+            for (int u = 0; u < NU; ++u) {
+            set_unit(u);
             float ssum = 0.f;
             // z0 of the next chunk is fetched before its accumulators are awaited: the loads do not depend on the conditioner
             constexpr int ZP = HW > 128 ? 8 : 32;  // prefetched z0 values per thread and chunk (beyond that: loaded in place)
@@ -970,7 +1056,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                 if ((lane & (SEG - 1)) == 0) red[warp * 2 + lane / SEG] = ssum;
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (tid < SPU) {
-                    const int bb = unit * SPU + tid;
+                    const int bb = (unit * NU + cu) * SPU + tid;
                     if (bb < B) {
                         float tot = 0.f;
                         if (HW > 128) {
@@ -1004,7 +1090,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     const int npix = SPU * g.HW;
                     for (int pp = tid; pp < npix; pp += kEpiThreads) {
                         const int sl = pp / g.HW, px = pp - sl * g.HW;
-                        const int bb = unit * SPU + sl;
+                        const int bb = (unit * NU + cu) * SPU + sl;
                         if (bb >= B) continue;
                         float* zp = zdst + static_cast<size_t>(bb) * g.D + px;
                         float vn[CP > 0 ? CP : 1];
@@ -1031,6 +1117,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                     }
                 }
             }
+            end_unit();
+            }  // units of this iteration
         }
         tl.stamp(42);
         tc_fence_before();
@@ -1148,22 +1236,24 @@ int pack_tc_launch(const float* pk_ffma, float* pk_tc_section, int Cin, int Cout
 // launch
 // =====================================================================================================================
 // `packed` = the whole buffer of nfb_resnet_pack: FFMA section | TF32 section | FP16-split section
-template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP = 0, bool F16 = false>
+template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP = 0, bool F16 = false, bool DUAL = false>
 static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* packed, const SplitGeom& g, int Cin, int Cout, int B,
                      const float* sa, const float* sb, int flags, cudaStream_t st, const PostOp& post = PostOp{}) {
-    using GM = TcGeom<H, W, PAIR, F16>;
+    using GM = TcGeom<H, W, PAIR, F16, DUAL>;
     const int dbg = (flags >> NFB_CONV_DEBUG_SHIFT) & 0xff;
     const int gq = (flags >> NFB_CONV_GROUPS_SHIFT) & 7;
     const int G = gq >= 1 && gq <= 4 ? gq : 3;  // accumulator groups per layer (at most the k-steps of a tap: 4 TF32 / 2 FP16)
     const TcPlan P = tc_plan(Cin, Cout, F16 ? 1 : 0);
     const float* pk_tc = packed + P.base;
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
-    const size_t smem = static_cast<size_t>(GM::ACT_BYTES) + 2 * slot_bytes(F16) + static_cast<size_t>((n_cst + 3) & ~3) * 4 + 9 * 8 + 8 + 64 + 2 * 9 * 16 + (2 * 9 + 1) * 5 * 16 +
+    const size_t smem = static_cast<size_t>(GM::NU * GM::ACT_BYTES) + 2 * slot_bytes(F16) + GM::XS_BYTES + static_cast<size_t>((n_cst + 3) & ~3) * 4 +
+                        ((4 + 5 * GM::NU) | 1) * 8 + 8 + 64 + 2 * 9 * 16 + 2 * GM::NU * GM::T * 9 * (1 + GM::NJ) * 16 +
                         (CP > 0 ? static_cast<size_t>(CP * CP + 2 * CP + 4) * 4 : 0);
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
-    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP, F16>;
+    if (DUAL && 2 * (FUSED ? P.NWf : P.NWg) > GM::TC) return NFB_ERR_UNSUPPORTED;  // output chunk wider than a tile's columns
+    auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP, F16, DUAL>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    const int n_units = (B + GM::SPU - 1) / GM::SPU;
+    const int n_units = ((B + GM::SPU - 1) / GM::SPU + GM::NU - 1) / GM::NU;
     const int grid = n_units < kSMs ? n_units : kSMs;
     kern<<<grid, kThreads, smem, st>>>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, post, G, dbg);
     return launch_status();
@@ -1172,7 +1262,16 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pa
 template <int MODE, bool FUSED, bool F16>
 static int tc_by_size_p(const float* zsrc, float* zdst, float* ldj, const float* pk_tc, const SplitGeom& g, int Cin, int Cout, int B,
                         int h, int w, const float* sa, const float* sb, int flags, cudaStream_t st) {
-    if (h == 16 && w == 16) return launch_tc<16, 16, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    if (h == 16 && w == 16) {
+        // two samples in flight per CTA (FP16 split only) when asked for (NFB_CONV_PAIR: throughput mode) or when the batch
+        // gives every SM more than one sample anyway; output layers wider than 64 columns per chunk stay on the one-unit kernel
+        const bool dual = F16 && ((flags & NFB_CONV_PAIR) ? B >= 2 : B > kSMs) && !(flags & NFB_CONV_SINGLE);
+        if (dual) {
+            const int rc = launch_tc<16, 16, MODE, FUSED, false, 0, F16, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+            if (rc != NFB_ERR_UNSUPPORTED) return rc;
+        }
+        return launch_tc<16, 16, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+    }
     // maps of <= 128 pixels: two tiles per CTA when asked for (NFB_CONV_PAIR: several batches in flight) or when the batch
     // alone gives every SM at least two single-tile units
     const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;

@@ -23,7 +23,10 @@ KEEP = re.compile(
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     key = sys.argv[3] if len(sys.argv) > 3 else None
-    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):  # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.csv
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = ['# ncu --set full --clock-control none summary of %s' % os.path.basename(rep)]
