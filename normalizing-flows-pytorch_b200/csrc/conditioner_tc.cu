@@ -408,8 +408,9 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     constexpr int ROWW = 1 + NJ;                                 // uint4 per row of the issue program
     constexpr int N_ROWS = 2 * NU * T * 9;                       // [weight slot][unit][tile][tap in issue order]
     uint4* prog = mask_tab + 2 * 9;                              // N_ROWS x [lane mask, NJ k-steps]: see below
+    uint4* prog_in = prog + N_ROWS * ROWW;                       // the same for the last pass of the input layer (nj_last k-steps)
     // CP > 0: Wt[ci][co], then exp(log_scale)[c], bias[c], 2 sums
-    float* wpost = reinterpret_cast<float*>(prog + N_ROWS * ROWW);
+    float* wpost = reinterpret_cast<float*>(prog_in + N_ROWS * ROWW);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) -> uint32_t { return bar0 + 8u * static_cast<uint32_t>(i); };
 
@@ -513,28 +514,30 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
         // tap in issue order): [lane mask | NJ x (A_hi descriptor, A_lo descriptor, B descriptor, TMEM address)].  The issuing
         // lane is a single thread whose instructions cost their full latency (~5 cycles each, measured): with these rows a
         // tap is 1 + NJ shared-memory loads, the register -> uniform-register moves and its MMAs, nothing else.
-        {
-            const int Ge = G < NJ ? G : NJ;
-            for (int r = lane; r < N_ROWS; r += 32) {
-                const int i = r % 9, t = (r / 9) % T, u = (r / (9 * T)) % NU, slot = r / (9 * T * NU);
-                const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
-                const int tap = static_cast<int>((order >> (4 * i)) & 15u);
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                prog[r * ROWW] = make_uint4(edge_mask<H, W>(t, dy, dx, 0), edge_mask<H, W>(t, dy, dx, 1),
-                                            edge_mask<H, W>(t, dy, dx, 2), edge_mask<H, W>(t, dy, dx, 3));
-                for (int j = 0; j < NJ; ++j) {
-                    const int kc = NJ * i + j;
-                    const uint32_t a_off = static_cast<uint32_t>(u * (GM::ACT_BYTES >> 4) + 2 * j * PB + GUARD + t * 128 + dy * W + dx);
-                    uint4 e;
-                    e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-                    e.y = (((smem_u32(act + NPL * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
-                    e.z = (((smem_u32(ring + slot * SLOT) >> 4) + static_cast<uint32_t>((tap * NJ + j) * 128)) & 0x3FFFu) | ((1024u >> 4) << 16);
-                    e.w = tmem + static_cast<uint32_t>(u * T * TC + t * TC + (kc % Ge) * 64);
-                    prog[r * ROWW + 1 + j] = e;
-                }
+        // A second table holds the last pass of the input layer (nj_last <= NJ k-steps per tap, its own weight offsets).
+        for (int r = lane; r < 2 * N_ROWS; r += 32) {
+            const bool in_layer = r >= N_ROWS;
+            const int rr = in_layer ? r - N_ROWS : r;
+            const int nj = in_layer ? P.nj_last : NJ;
+            const int Ge = G < nj ? G : nj;
+            const int i = rr % 9, t = (rr / 9) % T, u = (rr / (9 * T)) % NU, slot = rr / (9 * T * NU);
+            const uint64_t order = (LINKED && t == 1) ? kOrder1 : kOrder0;
+            const int tap = static_cast<int>((order >> (4 * i)) & 15u);
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            uint4* row = (in_layer ? prog_in : prog) + rr * ROWW;
+            row[0] = mask_tab[t * 9 + tap];
+            for (int j = 0; j < NJ; ++j) {
+                const int kc = nj * i + j;
+                const uint32_t a_off = static_cast<uint32_t>(u * (GM::ACT_BYTES >> 4) + 2 * j * PB + GUARD + t * 128 + dy * W + dx);
+                uint4 e;
+                e.x = (((smem_u32(act) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+                e.y = (((smem_u32(act + NPL * PS) >> 4) + a_off) & 0x3FFFu) | (static_cast<uint32_t>(PS >> 4) << 16);
+                e.z = (((smem_u32(ring + slot * SLOT) >> 4) + static_cast<uint32_t>((tap * nj + j) * 128)) & 0x3FFFu) | ((1024u >> 4) << 16);
+                e.w = tmem + static_cast<uint32_t>(u * T * TC + t * TC + (kc % Ge) * 64);
+                row[1 + j] = e;
             }
-            __syncwarp();
         }
+        __syncwarp();
         if (elect_one()) {
             const uint64_t dAH = make_smem_desc(smem_u32(act), PS, 128);
             const uint64_t dAL = make_smem_desc(smem_u32(act + NPL * PS), PS, 128);
@@ -583,29 +586,39 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         };
                         // taps order[i_lo .. i_hi) of tile t
                         auto issue = [&](int t, uint64_t order, int i_lo, int i_hi) {
-                            if (nj == NJ && !no_lo) {
+                            if (!no_lo && (nj == NJ || s == P.n_in - 1)) {
                                 // tabulated operands (see the prologue of this warp)
                                 if (no_mma) return;
                                 constexpr uint32_t hi32 = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-                                const uint4* pt = prog + (((slot * NU + cur_u) * T + t) * 9 + i_lo) * ROWW;
-                                auto tap_row = [&](const uint4* row, bool first) {
+                                const bool full = nj == NJ;
+                                const uint4* pt = (full ? prog : prog_in) + (((slot * NU + cur_u) * T + t) * 9 + i_lo) * ROWW;
+                                auto tap_row = [&](const uint4* row, bool first, bool all) {
                                     const uint4 m = row[0];
                                     uint4 e[NJ];
 #pragma unroll
-                                    for (int j = 0; j < NJ; ++j) e[j] = row[1 + j];
+                                    for (int j = 0; j < NJ; ++j)
+                                        if (all || j < nj) e[j] = row[1 + j];
 #pragma unroll
                                     for (int j = 0; j < NJ; ++j) {
-                                        const uint64_t b = (static_cast<uint64_t>(hi32) << 32) | e[j].z;
-                                        // the centre tap comes first: its first Ge k-steps start the accumulator groups
-                                        const uint32_t acc = (first && j < Ge) ? 0u : 1u;
-                                        mma_any<F16>(e[j].w, (static_cast<uint64_t>(hi32) << 32) | e[j].x, b, idesc_n<F16>(64), acc, m.x, m.y, m.z, m.w);
-                                        mma_any<F16>(e[j].w + 32, (static_cast<uint64_t>(hi32) << 32) | e[j].y, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
+                                        if (all || j < nj) {
+                                            const uint64_t b = (static_cast<uint64_t>(hi32) << 32) | e[j].z;
+                                            // the centre tap comes first: its first Ge k-steps start the accumulator groups
+                                            const uint32_t acc = (first && j < Ge) ? 0u : 1u;
+                                            mma_any<F16>(e[j].w, (static_cast<uint64_t>(hi32) << 32) | e[j].x, b, idesc_n<F16>(64), acc, m.x, m.y, m.z, m.w);
+                                            mma_any<F16>(e[j].w + 32, (static_cast<uint64_t>(hi32) << 32) | e[j].y, b, idesc_n<F16>(32), 1u, m.x, m.y, m.z, m.w);
+                                        }
                                     }
                                 };
                                 int i = i_lo;
-                                if (i == 0) { tap_row(pt, true); ++i; pt += ROWW; }
+                                if (full) {
+                                    if (i == 0) { tap_row(pt, true, true); ++i; pt += ROWW; }
 #pragma unroll 1
-                                for (; i < i_hi; ++i, pt += ROWW) tap_row(pt, false);
+                                    for (; i < i_hi; ++i, pt += ROWW) tap_row(pt, false, true);
+                                } else {
+                                    if (i == 0) { tap_row(pt, true, false); ++i; pt += ROWW; }
+#pragma unroll 1
+                                    for (; i < i_hi; ++i, pt += ROWW) tap_row(pt, false, false);
+                                }
                                 return;
                             }
                             const uint32_t tbase = tmem + uT + static_cast<uint32_t>(t * TC);
@@ -1247,7 +1260,7 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pa
     const float* pk_tc = packed + P.base;
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     const size_t smem = static_cast<size_t>(GM::NU * GM::ACT_BYTES) + 2 * slot_bytes(F16) + GM::XS_BYTES + static_cast<size_t>((n_cst + 3) & ~3) * 4 +
-                        ((4 + 5 * GM::NU) | 1) * 8 + 8 + 64 + 2 * 9 * 16 + 2 * GM::NU * GM::T * 9 * (1 + GM::NJ) * 16 +
+                        ((4 + 5 * GM::NU) | 1) * 8 + 8 + 64 + 2 * 9 * 16 + 2 * (2 * GM::NU * GM::T * 9 * (1 + GM::NJ) * 16) +
                         (CP > 0 ? static_cast<size_t>(CP * CP + 2 * CP + 4) * 4 : 0);
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
     if (DUAL && 2 * (FUSED ? P.NWf : P.NWg) > GM::TC) return NFB_ERR_UNSUPPORTED;  // output chunk wider than a tile's columns
