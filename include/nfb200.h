@@ -209,18 +209,25 @@ int nfb_resnet_pack(const float* const* tensors, float* packed, int in_ch, int o
 int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, int B, int C, int H, int W, int mode,
                     int odd, int in_ch, int out_ch, nfb_stream_t stream);
 /* Same with an explicit kernel selection (the library keeps no mutable state).  flags = 0 is nfb_convnet_fwd: the
- * tensor-core kernel (tcgen05, error-compensated TF32) where it applies (16x16 / 8x8 / 4x4), else the FP32-FFMA kernels.
+ * tensor-core kernel (tcgen05, error-compensated half-precision split: x = hi + 2^-10 lo, both fp16 -- the error of an
+ * fp32 convolution) where it applies (16x16 / 8x8 / 4x4), else the FP32-FFMA kernels.  Domain of the default operand format:
+ * |conditioner input|, |activation| and |folded weight| < 65504; beyond it the affected samples come back as NaN (never
+ * a finite wrong number) -- use NFB_CONV_TF32 or NFB_CONV_FFMA for such data.
  *   NFB_CONV_FFMA            use the FP32-FFMA kernels
+ *   NFB_CONV_TF32            tensor-core kernel with 3xTF32 operands (full fp32 range, ~1.25x the time at 16x16)
+ *   NFB_CONV_SINGLE          16x16 maps: one sample per CTA at a time (default: two in flight per CTA when the batch gives
+ *                            every SM more than one sample, or with NFB_CONV_PAIR)
  *   NFB_CONV_VARIANT_MASK    thread-tile variant of the FP32-FFMA kernel for this spatial size (0 = default)
- *   NFB_CONV_GROUPS(g)       accumulator groups per layer of the tensor-core kernel, 1..4 (0 = default 3)
+ *   NFB_CONV_GROUPS(g)       accumulator groups per layer of the tensor-core kernel, 1..4 (0 = default 3; at most the
+ *                            k-steps of one tap: 2 with the default operands, 4 with NFB_CONV_TF32)
  *   NFB_CONV_PAIR            8x8 / 4x4 maps: two independent 128-position tiles per CTA taking turns on the tensor core
  *                            (more work per SM-second, half the CTAs): for several batches in flight; without the flag
  *                            it is chosen only when the batch alone gives every SM two tiles
  *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results */
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
-#define NFB_CONV_TF32 0x10000 /* tensor-core kernel with 3xTF32 operands instead of the default FP16 split */
-#define NFB_CONV_SINGLE 0x20000 /* 16x16 maps: one sample per CTA at a time even when the batch would allow two in flight */
+#define NFB_CONV_TF32 0x10000
+#define NFB_CONV_SINGLE 0x20000
 #define NFB_CONV_PAIR 0x80
 #define NFB_CONV_GROUPS_SHIFT 4
 #define NFB_CONV_GROUPS(g) ((g) << NFB_CONV_GROUPS_SHIFT)
