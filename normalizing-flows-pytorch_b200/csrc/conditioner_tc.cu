@@ -361,7 +361,7 @@ struct TcGeom {
     static constexpr int TC = DUAL ? 128 : kTileCols;   // TMEM columns per tile (DUAL: 2 accumulator groups, out layer <= 128)
     static constexpr int XS_BYTES = DUAL ? NU * T * 32 * 128 * 4 : 0;  // residual stream [unit][tile][channel][row]
     static_assert(T <= 2 && NU * T * TC <= 512, "units exceed TMEM");
-    static_assert(!DUAL || (HW == 256 && F16 && !PAIR), "DUAL: 16x16 maps with FP16-split operands");
+    static_assert(!DUAL || (LINKED && F16), "DUAL: two-tile units with FP16-split operands");
     static_assert(HW == 256 || 128 % HW == 0, "tile must hold whole samples");
     static_assert(!(PAIR && HW > 128), "PAIR is for maps of at most 128 pixels");
 };
@@ -1290,6 +1290,10 @@ static int tc_by_size_p(const float* zsrc, float* zdst, float* ldj, const float*
     const long long tiles = (static_cast<long long>(B) * h * w + 127) / 128;
     const bool pair = (flags & NFB_CONV_PAIR) ? tiles >= 2 : tiles >= 2 * kSMs;
     if (h == 8 && w == 8) {
+        if (pair && F16 && tiles >= 4 && !(flags & NFB_CONV_SINGLE)) {  // two two-tile units in flight per CTA
+            const int rc = launch_tc<8, 8, MODE, FUSED, true, 0, F16, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
+            if (rc != NFB_ERR_UNSUPPORTED) return rc;
+        }
         if (pair) return launch_tc<8, 8, MODE, FUSED, true, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
         return launch_tc<8, 8, MODE, FUSED, false, 0, F16>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, flags, st);
     }
