@@ -222,9 +222,11 @@ class _ResNetConditioner(nn.Module):
 
 def set_throughput_mode(on=True):
     """Default kernel selection of every ConvNet conditioner that has no `kernel_flags` of its own.  on: several batches are
-    in flight (streams, one CUDA graph per stream): 8x8 / 4x4 maps run two tiles per CTA (NFB_CONV_PAIR), which does ~1.5x
-    the work per SM-second on half as many SMs.  off (default): one tile per CTA, the lowest latency of a single batch.
-    Captured CUDA graphs keep the choice they were captured with."""
+    in flight (streams, one CUDA graph per stream), so the cost of a kernel is the SM-time it occupies: two units per CTA
+    on every map size (NFB_CONV_PAIR: more work per SM-second on fewer SMs).  off (default): the lowest latency of a single
+    batch.  Results are the same to rounding.  Captured CUDA graphs keep the choice they were captured with.
+    (One launch per flow step -- Compose.fuse_steps = 2 -- is NOT part of it: measured 67.3 k vs 75.0 k samples/s on Glow-32,
+    the post-op's serial tail costs the conditioner CTAs more SM-time than the separate 1x1-conv launches take.)"""
     _ResNetConditioner.kernel_flags = L.CONV_PAIR if on else 0
 
 

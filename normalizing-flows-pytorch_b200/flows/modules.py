@@ -298,8 +298,11 @@ class Compose(nn.Module):
 
     # 1 (default): two launches per Glow step -- ActNorm + 1x1 conv, then the tensor-core conditioner with the affine coupling
     # as its epilogue, in place; 2: the conditioner kernel also applies the NEXT step's ActNorm + 1x1 conv (one launch per
-    # step where C <= 12; measured on B200: no faster than 1 -- the per-pixel matrix product runs on the 256 epilogue threads
-    # of <= 148 CTAs instead of the whole machine -- so it is not the default); 0: every layer through its own forward()
+    # flow step for every (map, channel) combination of the Glow stacks: 172 instead of 329 launches per Glow-32 step;
+    # measured on B200: slower than 1, 67.3 k vs 75.0 k samples/s with 5 batches in flight and no better for one batch -- the
+    # per-pixel matrix product runs as a serial tail on the 256 epilogue threads of the conditioner CTAs while their tensor
+    # pipe idles (ncu SM-time: +0.7 ms on the conditioner kernels for -0.4 ms of separate launches, warm) -- so it is not the
+    # default); 0: every layer through its own forward()
     fuse_steps = 1
 
     def __init__(self, layers):

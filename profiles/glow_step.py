@@ -1,8 +1,8 @@
 """Eager (no CUDA graph) steps of a bench workload, for ncu launch lists / full captures.
 
     ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
-        python profiles/glow_step.py [workload] [steps]
-(the profiled range -- cudaProfilerStart/Stop -- is the steps after the initialising forward)
+        python profiles/glow_step.py [workload] [steps] [throughput]
+(`throughput`: nfb200.set_throughput_mode(True), the kernel selection of the bench's 5-lane legs; the profiled range -- cudaProfilerStart/Stop -- is the steps after the initialising forward)
 """
 import os
 import sys
@@ -16,7 +16,10 @@ import nfb200  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'glow32'
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-model, dims, datatype, cfg, batch, desc = bench.WORKLOADS[wl]
+w = bench.WORKLOADS[wl]
+model, dims, datatype, cfg, batch = w['model'], w['dims'], w['datatype'], w['cfg'], w['batch']
+if len(sys.argv) > 3 and sys.argv[3] == 'throughput':
+    nfb200.set_throughput_mode(True)
 torch.manual_seed(0)
 net = getattr(nfb200, {'glow': 'Glow', 'flowpp': 'Flowpp', 'realnvp': 'RealNVP'}[model])(
     dims, datatype, types.SimpleNamespace(**cfg)).cuda().eval()
