@@ -227,6 +227,8 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
 #define NFB_CONV_TF32 0x10000
+#define NFB_CONV_ITERS_SHIFT 18 /* with NFB_CONV_PAIR: (1 + value) loop iterations per CTA (fewer, longer CTAs), value 0..3 */
+#define NFB_CONV_ITERS(n) ((n) << NFB_CONV_ITERS_SHIFT)
 #define NFB_CONV_SINGLE 0x20000
 #define NFB_CONV_PAIR 0x80
 #define NFB_CONV_GROUPS_SHIFT 4

@@ -21,6 +21,10 @@ CONV_TF32 = 0x10000
 CONV_SINGLE = 0x20000
 
 
+def conv_iters(n):
+    return (int(n) & 3) << 18
+
+
 def conv_variant(v):
     return v & 0x7
 

@@ -1167,7 +1167,15 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pa
     auto kern = convnet_tc_kernel<H, W, MODE, FUSED, PAIR, CP, F16, DUAL>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int n_units = ((B + GM::SPU - 1) / GM::SPU + GM::NU - 1) / GM::NU;
-    const int grid = n_units < kSMs ? n_units : kSMs;
+    int grid = n_units < kSMs ? n_units : kSMs;
+    // throughput mode: a CTA that runs several iterations pays the kernel prologue and the cold instruction cache once --
+    // less SM-time per sample on fewer SMs (the other batches in flight use the rest), at the price of this launch's latency
+    const int ipc = (flags >> NFB_CONV_ITERS_SHIFT) & 3;
+    if ((flags & NFB_CONV_PAIR) && ipc > 0 && n_units > 1) {
+        const int per = ipc + 1;
+        const int gq2 = (n_units + per - 1) / per;
+        if (gq2 < grid) grid = gq2;
+    }
     kern<<<grid, kThreads, smem, st>>>(zsrc, zdst, ldj, pk_tc, g, Cin, Cout, B, sa, sb, post, G, dbg);
     return launch_status();
 }
