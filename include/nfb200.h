@@ -227,7 +227,8 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
 #define NFB_CONV_TF32 0x10000
-#define NFB_CONV_ITERS_SHIFT 18 /* with NFB_CONV_PAIR: (1 + value) loop iterations per CTA (fewer, longer CTAs), value 0..3 */
+#define NFB_CONV_ITERS_SHIFT 18 /* with NFB_CONV_PAIR: (1 + value) loop iterations per CTA (fewer, longer CTAs), value 0..3;
+                                  measured on Glow-32 with 5 and 10 batches in flight: slower (75.0 k -> 62.9 k / 67.9 k samples/s) */
 #define NFB_CONV_ITERS(n) ((n) << NFB_CONV_ITERS_SHIFT)
 #define NFB_CONV_SINGLE 0x20000
 #define NFB_CONV_PAIR 0x80
@@ -239,8 +240,8 @@ int nfb_convnet_fwd_ex(const float* src, float* params_out, const float* packed,
                        int odd, int in_ch, int out_ch, int flags, nfb_stream_t stream);
 /* AffineCoupling.forward with its ConvNet conditioner as ONE kernel, in place on z (coupling.py:32-36,104-112 +
  * modules.py:416-438): z1 = pass-through half of z is gathered by the kernel, params = ConvNet(z1) is computed on the
- * tensor cores (tcgen05, error-compensated TF32) and consumed from tensor memory -- it never reaches shared or global
- * memory -- z0 <- z0*exp(tanh(s_raw)*a + b) + t is written over z0 inside z, ldj[b] += sum(s).  z1 stays untouched, so
+ * tensor cores (tcgen05, error-compensated FP16 split; NFB_CONV_TF32: 3xTF32) and consumed from tensor memory -- it
+ * never reaches shared or global memory -- z0 <- z0*exp(tanh(s_raw)*a + b) + t is written over z0 inside z, ldj[b] += sum(s).  z1 stays untouched, so
  * the result equals the reference's merged output.  `packed` from nfb_resnet_pack(in_ch = c0, out_ch = 2*c0).
  * Conditioner input sizes 16x16 / 8x8 / 4x4; otherwise (or with NFB_CONV_FFMA in flags) NFB_ERR_UNSUPPORTED: run
  * nfb_convnet_fwd + nfb_affine_coupling_fwd.  flags as for nfb_convnet_fwd_ex. */

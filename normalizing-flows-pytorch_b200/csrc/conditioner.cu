@@ -475,7 +475,7 @@ static int launch_cluster32(const float* zsrc, float* out, const float* pk, cons
 template <int MODE>
 static int dispatch_convnet(const float* zsrc, float* out, const float* pk, const SplitGeom& g, int Cin, int Cout, int B,
                             int h, int w, int flags, cudaStream_t st) {
-    if (!(flags & NFB_CONV_FFMA)) {  // default: tensor-core (tcgen05 3xTF32) kernel
+    if (!(flags & NFB_CONV_FFMA)) {  // default: tensor-core (tcgen05, split-precision) kernel
         const int rc = convnet_tc_dispatch(zsrc, out, pk, g, MODE, Cin, Cout, B, h, w, flags, st);
         if (rc != NFB_ERR_UNSUPPORTED) return rc;
     }

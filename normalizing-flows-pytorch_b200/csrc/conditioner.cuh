@@ -94,7 +94,7 @@ __device__ __forceinline__ void conv3x3_acc(float (&acc)[OCT][4], const float* _
     }
 }
 
-// ---- tensor-core (tcgen05, 3xTF32) section of the packed buffer, appended after the FFMA section -----------------
+// ---- tensor-core (tcgen05) sections of the packed buffer, appended after the FFMA section: 3xTF32, then FP16 split ---
 // All offsets in floats relative to `base`; every block is the exact shared-memory image the kernel's TMA copies fetch.
 //   consts   b0 | blk0: sA tA b1' b2 | blk1: sA tA b1' b2 | sO tO   (11 x 32 floats; b1' has the second BatchNorm of the
 //            block folded in, like the weights of its conv)

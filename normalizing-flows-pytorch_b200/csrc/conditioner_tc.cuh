@@ -1,9 +1,11 @@
-// conditioner_tc.cu -- the ConvNet conditioner (modules.py:416-438, weight_norm.py:35-45) on the 5th-generation tensor
+// conditioner_tc.cuh -- the ConvNet conditioner (modules.py:416-438, weight_norm.py:35-45) on the 5th-generation tensor
 // cores, optionally fused with AffineCoupling._transform (coupling.py:104-112) so that (t, s) never leave the SM.
+// (Kernel + launcher; included by conditioner_tc.cu and conditioner_tc_step.cu.)
 //
-// Arithmetic: every 3x3 / 1x1 layer is an implicit GEMM issued with tcgen05.mma (kind::tf32, M = 128 positions) by ONE
-// thread, accumulators in TMEM.  Single-pass TF32 misses the 1e-5 bits/dim bar, so every product is
-// error-compensated ("3xTF32"): x = x_hi + x_lo, x_hi = tf32(x) (round to nearest), x_lo = tf32(x - x_hi),
+// Arithmetic: every 3x3 / 1x1 layer is an implicit GEMM issued with tcgen05.mma (M = 128 positions) by ONE thread,
+// accumulators in TMEM.  Single-pass TF32 / FP16 misses the 1e-5 bits/dim bar, so every product is
+// error-compensated: x = x_hi + x_lo with 11 significant bits each (TF32: x_hi = tf32(x), x_lo = tf32(x - x_hi); the default
+// FP16 split is described further down),
 //     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi            (the dropped a_lo*b_lo is ~2^-24 relative).
 // The GEMM is skinny (N = 32 output channels) and in SS mode every MMA re-reads its 4 KB A tile from shared memory,
 // so the operand B is N-CONCATENATED: rows [w_hi | w_lo] give a_hi*b_hi and a_hi*b_lo from ONE A read (N = 64), and

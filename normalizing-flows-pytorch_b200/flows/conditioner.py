@@ -227,8 +227,7 @@ def set_throughput_mode(on=True):
     batch.  Results are the same to rounding.  Captured CUDA graphs keep the choice they were captured with.
     (One launch per flow step -- Compose.fuse_steps = 2 -- is NOT part of it: measured 67.3 k vs 75.0 k samples/s on Glow-32,
     the post-op's serial tail costs the conditioner CTAs more SM-time than the separate 1x1-conv launches take.)"""
-    import os
-    _ResNetConditioner.kernel_flags = (L.CONV_PAIR | L.conv_iters(int(os.environ.get('NFB200_ITERS', '0')))) if on else 0
+    _ResNetConditioner.kernel_flags = L.CONV_PAIR if on else 0
 
 
 class MLP(_ResNetConditioner):
