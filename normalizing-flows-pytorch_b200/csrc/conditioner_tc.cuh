@@ -405,8 +405,8 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
     // ([unit][tile] for ACT_READY / ACC_DONE; an odd count keeps the 16-byte alignment of the tables behind the barriers)
     constexpr int W_FULL = 0, W_EMPTY = 2, ACT_READY = 4, ACC_DONE = 4 + 2 * NU, WAR0 = 4 + 4 * NU, N_BARS = (4 + 5 * NU) | 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [8 warps][2]
-    uint4* mask_tab = reinterpret_cast<uint4*>(red + 16);        // [T][9 taps]: rows of the tile whose tap leaves the image
+    float* red_all = reinterpret_cast<float*>(tmem_slot + 2);   // [NU units][8 warps][2]
+    uint4* mask_tab = reinterpret_cast<uint4*>(red_all + 16 * NU);        // [T][9 taps]: rows of the tile whose tap leaves the image
     constexpr int ROWW = 1 + NJ;                                 // uint4 per row of the issue program
     constexpr int N_ROWS = 2 * NU * T * 9;                       // [weight slot][unit][tile][tap in issue order]
     uint4* prog = mask_tab + 2 * 9;                              // N_ROWS x [lane mask, NJ k-steps]: see below
@@ -1066,12 +1066,16 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
             if (FUSED) {
                 // per-sample log-det: fixed-order reduction (segmented shuffle -> shared memory -> one thread per sample)
                 constexpr int SEG = HW < 32 ? HW : 32;
+                float* red = red_all + 16 * cu;  // one array per unit in flight: no barrier is needed before its next use
+                const int bb_l = (unit * NU + cu) * SPU + tid;
+                float ldj_old = 0.f;
+                if (tid < SPU && bb_l < B) ldj_old = ldj[bb_l];  // issued before the barrier: its latency hides behind it
 #pragma unroll
                 for (int o = SEG / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
                 if ((lane & (SEG - 1)) == 0) red[warp * 2 + lane / SEG] = ssum;
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (tid < SPU) {
-                    const int bb = (unit * NU + cu) * SPU + tid;
+                    const int bb = bb_l;
                     if (bb < B) {
                         float tot = 0.f;
                         if (HW > 128) {
@@ -1085,7 +1089,7 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         } else if (HW == 16) tot = red[(tid >> 1) * 2 + (tid & 1)] + red[((tid >> 1) + 4) * 2 + (tid & 1)];
                         else if (HW == 64) tot = (red[(2 * tid) * 2] + red[(2 * tid + 1) * 2]) + (red[(2 * tid + 4) * 2] + red[(2 * tid + 5) * 2]);
                         else tot = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
-                        float l = __fadd_rn(ldj[bb], tot);  // coupling.py:110
+                        float l = __fadd_rn(ldj_old, tot);  // coupling.py:110
                         if (CP > 0) {
                             const float hw_full = static_cast<float>(g.HW);
                             l = __fadd_rn(l, __fmul_rn(wpost[CP * CP + 2 * CP], hw_full));      // ActNorm, modules.py:249
@@ -1094,8 +1098,12 @@ convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __res
                         ldj[bb] = l;
                     }
                 }
-                if (CP > 0) __threadfence_block();  // this CTA's z0 stores are visible to all its threads after the barrier
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                // (the next write to this unit's `red` is a whole unit of mbarrier handshakes away, all of which this thread's
+                // warp takes part in: no second barrier unless the post-op below needs this CTA's z stores)
+                if (CP > 0) {
+                    __threadfence_block();  // this CTA's z0 stores are visible to all its threads after the barrier
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                }
                 if (CP > 0) {
                     // next step's ActNorm + 1x1 conv, in place: thread = pixel; the CP normalised inputs stay in registers, the
                     // outputs are produced one channel at a time (rolled loop over co, unrolled dot product over ci: the same
@@ -1162,7 +1170,7 @@ static int launch_tc(const float* zsrc, float* zdst, float* ldj, const float* pa
     const float* pk_tc = packed + P.base;
     const int n_cst = 352 + (FUSED ? P.nqf * P.NWf : P.nqg * P.NWg);
     const size_t smem = static_cast<size_t>(GM::NU * GM::ACT_BYTES) + 2 * slot_bytes(F16) + GM::XS_BYTES + static_cast<size_t>((n_cst + 3) & ~3) * 4 +
-                        ((4 + 5 * GM::NU) | 1) * 8 + 8 + 64 + 2 * 9 * 16 + 2 * (2 * GM::NU * GM::T * 9 * (1 + GM::NJ) * 16) +
+                        ((4 + 5 * GM::NU) | 1) * 8 + 8 + 64 * GM::NU + 2 * 9 * 16 + 2 * (2 * GM::NU * GM::T * 9 * (1 + GM::NJ) * 16) +
                         (CP > 0 ? static_cast<size_t>(CP * CP + 2 * CP + 4) * 4 : 0);
     if (smem > 227 * 1024) return NFB_ERR_UNSUPPORTED;
     if (DUAL && 2 * (FUSED ? P.NWf : P.NWg) > GM::TC) return NFB_ERR_UNSUPPORTED;  // output chunk wider than a tile's columns
