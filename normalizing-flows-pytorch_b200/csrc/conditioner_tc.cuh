@@ -308,11 +308,14 @@ __device__ __forceinline__ int half_elem_offset(const SplitGeom& g, int m, int s
     return (k >> 2) * g.HW + (2 * i + ((k >> 1) & 1)) * g.W + 2 * j + (k & 1);
 }
 
-// developer timeline: when set (nfb_debug_timeline), CTA 0 records clock64() stamps: [role 0 = epilogue thread 0,
-// 1 = epilogue thread 128, 2 = MMA lane 0, 3 = kernel entry / prologue done / exit][event index] = (tag << 48) | (clock & 0xffffffffffff)
+// developer timeline (builds with -DNFB_TC_TIMELINE only: `make EXTRA=-DNFB_TC_TIMELINE`; profiles/tc2_timeline.py): when set
+// (nfb_debug_timeline), CTA 0 records clock64() stamps: [role 0 = epilogue thread 0, 1 = epilogue thread 128, 2 = MMA lane 0,
+// 3 = kernel entry / prologue done / exit][event index] = (tag << 48) | (clock & 0xffffffffffff).  In the normal build the
+// stamps compile to nothing: the MMA lane pays ~5 cycles for every instruction it executes, also for a not-taken branch.
 static __device__ unsigned long long* g_tl_buf = nullptr;
 constexpr int kTlEvents = 512;
 struct Timeline {
+#ifdef NFB_TC_TIMELINE
     unsigned long long* p;
     int n;
     __device__ __forceinline__ void init(int role, bool on) {
@@ -324,6 +327,10 @@ struct Timeline {
             p[n++] = (static_cast<unsigned long long>(tag) << 48) | (static_cast<unsigned long long>(clock64()) & 0xffffffffffffull);
         }
     }
+#else
+    __device__ __forceinline__ void init(int, bool) {}
+    __device__ __forceinline__ void stamp(int) {}
+#endif
 };
 
 // tap issue order: centre first (its first Ge k-steps start the accumulator groups with accumulate = 0, unmasked);

@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of the tensor-core conditioner (developer instrumentation):
+"""Timeline of CTA 0 of the tensor-core conditioner (developer instrumentation; needs a library built with
+`make -C normalizing-flows-pytorch_b200/csrc EXTRA=-DNFB_TC_TIMELINE` -- the stamps are compiled out otherwise):
 python profiles/tc2_timeline.py CIN COUT HW B [dbg] [fused: checker|channel|none] [extra kernel flags, e.g. 0x10000 = 3xTF32]"""
 import ctypes
 import os
