@@ -223,7 +223,8 @@ int nfb_convnet_fwd(const float* src, float* params_out, const float* packed, in
  *   NFB_CONV_PAIR            8x8 / 4x4 maps: two independent 128-position tiles per CTA taking turns on the tensor core
  *                            (more work per SM-second, half the CTAs): for several batches in flight; without the flag
  *                            it is chosen only when the batch alone gives every SM two tiles
- *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results */
+ *   NFB_CONV_DEBUG(bits)     profiling knobs of the tensor-core kernel (skip MMAs / TMEM loads / ...): WRONG results; honoured
+ *                            only by a library built with -DNFB_TC_DEBUG_KNOBS, ignored otherwise */
 #define NFB_CONV_VARIANT_MASK 0x7
 #define NFB_CONV_FFMA 0x8
 #define NFB_CONV_TF32 0x10000

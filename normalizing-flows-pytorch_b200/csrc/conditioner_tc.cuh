@@ -393,7 +393,15 @@ struct PostOp {
 template <int H, int W, int MODE, bool FUSED, bool PAIR, int CP, bool F16, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 convnet_tc_kernel(const float* zsrc, float* zdst, float* ldj, const float* __restrict__ pk, SplitGeom g, int Cin, int Cout,
-                  int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, PostOp post, int G, int dbg) {
+                  int B, const float* __restrict__ p_sa, const float* __restrict__ p_sb, PostOp post, int G, int dbg_arg) {
+    // profiling knobs (NFB_CONV_DEBUG: skip MMAs / TMEM loads / activation stores / weight traffic -- WRONG results) exist in
+    // builds with -DNFB_TC_DEBUG_KNOBS only; in the normal build they fold to constants (the MMA lane pays for every branch)
+#ifdef NFB_TC_DEBUG_KNOBS
+    const int dbg = dbg_arg;
+#else
+    constexpr int dbg = 0;
+    (void)dbg_arg;
+#endif
     using GM = TcGeom<H, W, PAIR, F16, DUAL>;
     constexpr int HW = GM::HW, T = GM::T, SPT = GM::SPT, SPU = GM::SPU, CS = GM::CS, NCH = GM::NCH, GUARD = GM::GUARD,
                   PB = GM::PB, PS = GM::PS, NPL = GM::NPL, NJ = GM::NJ, NU = GM::NU, TC = GM::TC;

@@ -1,5 +1,6 @@
 """Diagnostics of the tensor-core conditioner (csrc/conditioner_tc.cu) on a B200: error against the fp64 CPU oracle and
 the FP32-FFMA kernel, fused conditioner+coupling against the two-kernel path, and CUDA-event timings per shape.
+(The "knobs" lines need a library built with `make EXTRA=-DNFB_TC_DEBUG_KNOBS`; otherwise every knob column is the full kernel.)
 
     python profiles/tc2_probe.py [--quick]
 """
