@@ -710,7 +710,7 @@ def run_nfb200(args, rank, world, local_rank):
         'run': {'l2': 'inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)' % (ring_n, ring_n * bytes_per_batch / 1e6),
                 'parallelism': 'sample-sharded replicas x%d; one all-reduce of K x (sum NLL, count) per timed window' % world,
                 'batches_in_flight': n_lanes,
-                'kernel_selection': 'throughput mode (nfb200.set_throughput_mode: two tiles per CTA on 8x8 / 4x4 conditioner maps) '
+                'kernel_selection': 'throughput mode (nfb200.set_throughput_mode: two units in flight per CTA on every conditioner map size) '
                                     'for the %d-lane legs; latency mode for single_stream and inverse' % n_lanes,
                 'timing': 'CUDA events around K graph replays (%d batches in flight on %d streams), max over ranks' % (n_lanes, n_lanes),
                 'wall_s': wall},
